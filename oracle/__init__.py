@@ -1,0 +1,25 @@
+"""
+TEST INFRASTRUCTURE ONLY -- not product code.
+
+CPU oracles for the non-local-means hot path of jnhansen/nd
+(`nd/_filters.pyx::_pixelwise_nlmeans_3d`).  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference`
+legs may import anything from this package; `nd_b200` (the product) never does.
+
+Three oracles, in decreasing order of authority:
+
+1. `oracle.ref`       -- the reference's OWN Cython kernel, compiled unmodified from
+                         `/root/reference/nd/_filters.pyx` into `oracle/_ref/` by
+                         `oracle/build_ref.py` (git-ignored, travels to the GPU box).
+                         Pins both semantics (see `oracle.ref` docstring):
+                         `reference_compiled` by a direct call and `as_written` through the
+                         pad+augment+crop construction.
+2. `oracle.c_port`    -- a plain-C restatement (`oracle/nlm_oracle.c`), pinned against (1)
+                         by `tests/test_oracle.py` and by the committed golden vectors in
+                         `tests/golden/`.  Fast enough for the CPU-baseline timing.
+3. `oracle.nlm_numpy` -- an independent float64 NumPy restatement in the box-sum form the
+                         CUDA kernels use.
+
+Parity status: PINNED -- every oracle is checked against outputs of the unmodified
+reference kernel run in this container (`tests/golden/make_golden.py`).
+"""
