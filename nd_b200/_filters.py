@@ -1,0 +1,134 @@
+"""
+Drop-in for `nd._filters` (reference nd/_filters.pyx): the same entry point, same argument
+meaning and error behaviour, on host NumPy arrays -- but the arithmetic runs on the GPU through
+libndnlm.so (include/ndnlm.h).  There is no CPU fallback: without a CUDA device or without the
+built library this raises.
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+
+
+def find_weight(weight_sum, sq_weight_sum, n):
+    """Closed form of reference nd/_filters.pyx:297-314 (host scalar helper; the kernels
+    evaluate the same expression per voxel on the device)."""
+    if n - 1 > weight_sum ** 2 / sq_weight_sum:
+        raise ValueError('No solution')
+    rt = math.sqrt(n * weight_sum * weight_sum - n * n * sq_weight_sum + n * sq_weight_sum)
+    return (weight_sum + rt) / (n - 1)
+
+
+def _as_u32_3(x, name):
+    a = np.asarray(x)
+    if isinstance(x, np.ndarray) and a.dtype != np.uint32:
+        # the reference's typed memoryview `unsigned int[:]` rejects other dtypes (nd/_filters.pyx:322-323)
+        raise ValueError("Buffer dtype mismatch, expected 'unsigned int' but got '%s' for %s" % (a.dtype, name))
+    if a.ndim != 1 or a.shape[0] != 3:
+        raise ValueError('%s must have exactly 3 entries (one per array axis)' % name)
+    if np.any(np.asarray(a, dtype=np.int64) < 0):
+        raise ValueError('%s must be non-negative' % name)
+    return tuple(int(v) for v in a)
+
+
+def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=None, kernel='auto',
+                          njobs=1, shard_axis=None):
+    """
+    GPU replacement of `nd._filters._pixelwise_nlmeans_3d` (reference nd/_filters.pyx:320-420).
+
+    arr, output : (N0, N1, N2, V) float32 or float64 NumPy arrays (any strides); `output` is written
+                  in place.  Other dtypes raise TypeError like the fused `floating` signature.
+    r, f        : 3 search / patch radii (uint32 arrays as in the reference, or sequences).
+    sigma, h, n_eff : as in the reference; n_eff < 0 means self weight = max weight.
+    semantics   : 'as_written' (default) or 'reference_compiled' (SURVEY.md D1); also ND_NLM_SEMANTICS.
+    njobs       : number of GPUs to shard over along `shard_axis` (default: the largest axis that is
+                  not filtered, else the largest axis -- reference nd/filters.py:424-435).
+    """
+    import torch
+    from . import device as dev
+
+    arr = np.asarray(arr) if not isinstance(arr, np.ndarray) else arr
+    if not isinstance(output, np.ndarray):
+        raise TypeError('output must be a NumPy array (it is written in place)')
+    if arr.dtype not in (np.float32, np.float64) or output.dtype != arr.dtype:
+        raise TypeError('No matching signature found')          # fused-type dispatch failure in the reference
+    if arr.ndim != 4 or output.ndim != 4:
+        raise ValueError('Buffer has wrong number of dimensions (expected 4, got %d)' % arr.ndim)
+    if output.shape != arr.shape:
+        raise ValueError('output shape %s does not match input shape %s' % (output.shape, arr.shape))
+    r3 = _as_u32_3(r, 'r')
+    f3 = _as_u32_3(f, 'f')
+    _lib.lib()                                                  # fail loudly if the library is missing
+    if not torch.cuda.is_available():
+        raise RuntimeError('nd_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    if arr.size == 0:
+        return
+
+    if any(s < 0 for s in arr.strides):
+        arr = np.ascontiguousarray(arr)
+    njobs = int(njobs)
+    if njobs == -1:
+        njobs = torch.cuda.device_count()
+    if njobs > 1:
+        _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis)
+        return
+
+    plan = dev.Plan(arr.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)
+    d_in = torch.from_numpy(arr).cuda()
+    d_out = torch.empty_like(d_in)
+    plan.apply(d_in, d_out)
+    _copy_back(output, d_out)
+
+
+def _copy_back(output, d_out):
+    import torch
+    if all(s >= 0 for s in output.strides) and output.flags.writeable:
+        torch.from_numpy(output).copy_(d_out)
+    else:
+        output[...] = d_out.cpu().numpy()
+
+
+def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis):
+    """Single-process multi-GPU apply: shard along one axis, halo rows over NVLink peer copies."""
+    import torch
+    from . import device as dev
+    from .shard import ShardPlan, exchange_halos_p2p
+
+    ndev = torch.cuda.device_count()
+    if njobs > ndev:
+        raise ValueError('njobs=%d but only %d CUDA devices are visible' % (njobs, ndev))
+    if shard_axis is None:
+        free = [a for a in range(3) if r3[a] == 0 and f3[a] == 0]
+        cand = free if free else [0, 1, 2]
+        shard_axis = max(cand, key=lambda a: arr.shape[a])
+    halo = r3[shard_axis] + f3[shard_axis]
+    sp = ShardPlan(arr.shape[shard_axis], njobs, halo)
+    plans, paddeds, outs, flags, slabs = [], [], [], [], []
+    for i, (lo, hi) in enumerate(sp.ranges):
+        idx = [slice(None)] * 4
+        idx[shard_axis] = slice(lo, hi)
+        slab = arr[tuple(idx)]
+        with torch.cuda.device(i):
+            plan = dev.Plan(slab.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)
+            d_in = torch.from_numpy(slab).to('cuda:%d' % i, non_blocking=True)
+            padded = plan.new_padded(d_in.device)
+            lo_e, hi_e = sp.edges(i)
+            plan.stage(d_in, padded, shard_axis, lo_e, hi_e)
+        plans.append(plan); paddeds.append(padded); slabs.append((idx, d_in))
+    exchange_halos_p2p(plans, paddeds, shard_axis)
+    for i, plan in enumerate(plans):
+        with torch.cuda.device(i):
+            internal = plan.new_internal_out(paddeds[i].device)
+            flag = torch.zeros(1, dtype=torch.int32, device=paddeds[i].device)
+            plan.run(paddeds[i], internal, flag)
+            d_out = torch.empty_like(slabs[i][1])
+            plan.unstage(internal, d_out)
+        outs.append(d_out); flags.append(flag)
+    bad = False
+    for i, d_out in enumerate(outs):
+        torch.cuda.synchronize(i)
+        bad = bad or bool(flags[i].item())
+        output[tuple(slabs[i][0])] = d_out.cpu().numpy()
+    if bad:
+        raise ValueError('No solution')

@@ -1,0 +1,543 @@
+// ndnlm.cu -- C ABI (include/ndnlm.h) over the sm_100a non-local-means kernels.
+//
+// Replaces nd/_filters.pyx::_pixelwise_nlmeans_3d (reference nd/_filters.pyx:317-420) behind the
+// call site nd/filters.py:462-463.  See include/ndnlm.h for the contract of every entry point.
+#include "../../include/ndnlm.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "nlm_common.cuh"
+#include "nlm_generic.cuh"
+#include "nlm_staging.cuh"
+#include "nlm_tiled.cuh"
+
+using namespace ndnlm;
+
+// ------------------------------------------------------------------------------------------
+// errors, launch accounting
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(NDNLM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static inline unsigned blocks_for(long long total, int threads) { return unsigned((total + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------
+// tiled-kernel instantiation table
+// ------------------------------------------------------------------------------------------
+typedef cudaError_t (*tiled_launch_fn)(const CUtensorMap&, const DevParams&, const float4*, float4*, int*, int grid,
+                                       size_t smem, cudaStream_t);
+
+template <int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
+static cudaError_t launch_tiled(const CUtensorMap& tmap, const DevParams& P, const float4* padded, float4* out,
+                                int* err, int grid, size_t smem, cudaStream_t st) {
+    auto kern = nlm_tiled_kernel<NV4, FW, FX, FR, L, NWARPS, CH, NEFF>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    });
+    if (attr_err != cudaSuccess) return attr_err;
+    kern<<<grid, NWARPS * 32, smem, st>>>(tmap, P, padded, out, err);
+    return cudaGetLastError();
+}
+
+struct TiledInst {
+    int nv4, fw, fx, fr, L, nwarps, ch;
+    bool neff;
+    size_t exch_bytes;
+    tiled_launch_fn launch;
+    const char* name;
+};
+
+#define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
+    {                                                                                                \
+        NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES,     \
+            launch_tiled<NV4, FW, FX, FR, L, NW, CH, NEFF>,                                          \
+            "nlm_tiled<nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
+    }
+
+// Candidates are tried in order; the first whose shared-memory box fits is used.
+static const TiledInst g_tiled[] = {
+#include "nlm_tiled_instances.inc"
+};
+static const int g_ntiled = int(sizeof(g_tiled) / sizeof(g_tiled[0]));
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+struct ndnlm_plan {
+    int64_t shape[4];
+    uint32_t r[3], f[3];
+    double sigma, h, n_eff;
+    int semantics, dtype;
+    int perm[3];        // role -> user axis
+    DevParams P;
+    int kernel;         // NDNLM_KERNEL_GENERIC / NDNLM_KERNEL_TILED
+    int inst;           // index into g_tiled
+    int threads, grid;
+    size_t smem;
+    int elem_bytes;
+    size_t padded_bytes, out_bytes;
+    double flops_per_voxel;
+    int64_t n_offsets;
+    char name[96];
+};
+
+static const size_t kMaxSmem = 232448;   // 227 KB per CTA on sm_100a
+
+static int largest_divisor_leq(int n, int cap) {
+    int best = 1;
+    for (int d = 1; d <= n; ++d)
+        if (n % d == 0 && d <= cap) best = d;
+    return best;
+}
+
+// Try to configure tiled instantiation `ti` for the plan's geometry; returns true if it fits.
+static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti) {
+    DevParams& P = pl->P;
+    if (ti.nv4 != P.nv4) return false;
+    if (ti.fw != P.fr[0] || ti.fr != P.fr[1] || ti.fx != P.fr[2]) return false;
+    if (ti.neff != (pl->n_eff >= 0)) return false;
+    const int txw = 32 - 2 * ti.fx;
+    int gw, gr, gx;
+    if (ti.fw > 0) {
+        gw = ti.nwarps;
+        gr = gx = 1;
+    } else {
+        gw = largest_divisor_leq(ti.nwarps, P.n[0] < 1 ? 1 : P.n[0]);
+        const int rem = ti.nwarps / gw;
+        gx = 1;
+        for (int d = 1; d <= rem; ++d)
+            if (rem % d == 0 && (long long)(d - 1) * txw < P.n[2] && d * txw + 2 * ti.fx + 2 * P.rad[2] <= 256) gx = d;
+        gr = rem / gx;
+    }
+    P.g[0] = gw; P.g[1] = gr; P.g[2] = gx;
+    P.t[0] = gw - 2 * ti.fw; P.t[1] = gr * ti.L; P.t[2] = gx * txw;
+    if (P.t[0] < 1) return false;
+    P.b[0] = gw + 2 * P.rad[0];
+    P.b[1] = gr * ti.L + 2 * ti.fr + 2 * P.rad[1];
+    P.b[2] = gx * txw + 2 * ti.fx + 2 * P.rad[2];
+    for (int k = 0; k < 3; ++k)
+        if (P.b[k] > 256) return false;
+    long long tiles = 1;
+    for (int k = 0; k < 3; ++k) {
+        P.tiles[k] = (P.n[k] + P.t[k] - 1) / P.t[k];
+        tiles *= P.tiles[k];
+    }
+    if (tiles > 0x7fffffffLL) return false;
+    const size_t plane = ((size_t(P.b[0]) * P.b[1] * P.b[2] + 7) / 8) * 8;
+    const size_t smem = size_t(ti.nv4) * plane * 16 + ti.exch_bytes + 16;
+    if (smem > kMaxSmem) return false;
+    pl->smem = smem;
+    pl->threads = ti.nwarps * 32;
+    pl->grid = int(tiles);
+    return true;
+}
+
+extern "C" int ndnlm_plan_create(ndnlm_plan_t** out_plan, const int64_t shape[4], const uint32_t r[3],
+                                 const uint32_t f[3], double sigma, double h, double n_eff, int semantics,
+                                 int dtype, int kernel) {
+    if (!out_plan || !shape || !r || !f) return fail(NDNLM_EINVAL, "null argument");
+    *out_plan = nullptr;
+    if (dtype != NDNLM_F32 && dtype != NDNLM_F64)
+        return fail(NDNLM_EDTYPE, "No matching signature found (only float32 / float64 data is supported)");
+    if (semantics != NDNLM_AS_WRITTEN && semantics != NDNLM_REFERENCE_COMPILED)
+        return fail(NDNLM_EINVAL, "unknown semantics %d", semantics);
+    for (int a = 0; a < 4; ++a)
+        if (shape[a] < 1 || shape[a] > 0x3fffffff) return fail(NDNLM_EINVAL, "shape[%d]=%lld out of range", a, (long long)shape[a]);
+    for (int a = 0; a < 3; ++a) {
+        if ((int64_t)r[a] + (int64_t)f[a] > shape[a] - 1)
+            return fail(NDNLM_ERADIUS, "r[%d]+f[%d]=%u exceeds N-1=%lld: a single reflection is undefined there", a, a,
+                        r[a] + f[a], (long long)shape[a] - 1);
+    }
+    if (!(h != 0.0)) return fail(NDNLM_EINVAL, "h must be non-zero");
+    if (n_eff >= 0 && n_eff == 1.0) return fail(NDNLM_EINVAL, "n_eff == 1 divides by zero in find_weight");
+
+    ndnlm_plan* pl = new ndnlm_plan();
+    memset(pl, 0, sizeof(*pl));
+    for (int a = 0; a < 4; ++a) pl->shape[a] = shape[a];
+    for (int a = 0; a < 3; ++a) { pl->r[a] = r[a]; pl->f[a] = f[a]; }
+    pl->sigma = sigma; pl->h = h; pl->n_eff = n_eff; pl->semantics = semantics; pl->dtype = dtype;
+
+    // ---- role assignment: X = widest active axis, R = remaining active axis with the smallest search
+    //      radius, W = the rest (ties go to the later, i.e. faster-varying, axis) ----
+    bool active[3];
+    int nact = 0;
+    for (int a = 0; a < 3; ++a) { active[a] = (r[a] > 0 || f[a] > 0); nact += active[a]; }
+    int ax = -1, ar = -1, aw = -1;
+    auto pick = [&](bool want_active, bool any, auto better) {
+        int best = -1;
+        for (int a = 0; a < 3; ++a) {
+            if (a == ax || a == ar) continue;
+            if (!any && active[a] != want_active) continue;
+            if (best < 0 || better(a, best)) best = a;
+        }
+        return best;
+    };
+    auto larger_n = [&](int a, int b) { return shape[a] >= shape[b]; };
+    auto smaller_r = [&](int a, int b) { return r[a] < r[b] || (r[a] == r[b] && shape[a] <= shape[b]); };
+    ax = pick(true, nact == 0, larger_n);
+    if (nact >= 2) ar = pick(true, false, smaller_r);
+    else ar = pick(false, true, larger_n);
+    aw = pick(false, true, larger_n);
+    pl->perm[ROLE_W] = aw; pl->perm[ROLE_R] = ar; pl->perm[ROLE_X] = ax;
+
+    DevParams& P = pl->P;
+    int n_a = 0;
+    long long K = 1;
+    for (int role = 0; role < 3; ++role) {
+        const int a = pl->perm[role];
+        P.n[role] = int(shape[a]);
+        P.rad[role] = int(r[a]);
+        P.fr[role] = int(f[a]);
+        P.pad[role] = int(r[a] + f[a]);
+        P.pd[role] = P.n[role] + 2 * P.pad[role];
+        n_a += f[a] > 0;
+        K *= 2 * (long long)r[a] + 1;
+    }
+    K -= 1;
+    const int V = int(shape[3]);
+    P.V = V;
+    P.nv4 = (V + 3) / 4;
+    const double norm = double(V) * (2.0 * f[0] + 1) * (2.0 * f[1] + 1) * (2.0 * f[2] + 1);
+    P.inv_norm = 1.0 / norm;
+    P.two_sigma2 = 2.0 * sigma * sigma;
+    P.inv_h2 = 1.0 / (h * h);
+    P.n_eff = n_eff;
+    const double log2e = 1.4426950408889634;
+    P.c1 = float(log2e / (norm * h * h));
+    P.c2 = float(2.0 * sigma * sigma * log2e / (h * h));
+    P.zero_dist = (semantics == NDNLM_REFERENCE_COMPILED) && (f[0] > 0 || f[1] > 0 || f[2] > 0);
+    {
+        const char* env = getenv("NDNLM_LOADER");
+        P.use_ldg_loader = (env && strcmp(env, "ldg") == 0) ? 1 : 0;
+    }
+    pl->n_offsets = K;
+    pl->flops_per_voxel = double(K) * (5.0 * V + 2.0 * n_a + 6.0 + (n_eff >= 0 ? 2.0 : 0.0)) + 3.0 * V + 3.0;
+
+    // ---- kernel selection ----
+    pl->kernel = NDNLM_KERNEL_GENERIC;
+    pl->inst = -1;
+    const bool tiled_ok = (dtype == NDNLM_F32) && !P.zero_dist && K > 0;
+    if (kernel != NDNLM_KERNEL_GENERIC && tiled_ok) {
+        const char* venv = getenv("NDNLM_TILED_VARIANT");   // tuning aid: force one instantiation
+        const int forced = venv ? atoi(venv) : -1;
+        for (int i = 0; i < g_ntiled; ++i) {
+            if (forced >= 0 && i != forced) continue;
+            if (configure_tiled(pl, g_tiled[i])) {
+                pl->kernel = NDNLM_KERNEL_TILED;
+                pl->inst = i;
+                break;
+            }
+        }
+    }
+    if (kernel == NDNLM_KERNEL_TILED && pl->kernel != NDNLM_KERNEL_TILED) {
+        delete pl;
+        return fail(NDNLM_EINVAL, "no tiled-kernel instantiation for this configuration (dtype/V/f pattern/shared memory)");
+    }
+    const long long voxels = (long long)shape[0] * shape[1] * shape[2];
+    const long long pvox = (long long)P.pd[0] * P.pd[1] * P.pd[2];
+    if (pl->kernel == NDNLM_KERNEL_TILED) {
+        pl->elem_bytes = 4;
+        pl->padded_bytes = size_t(pvox) * P.nv4 * 16;
+        pl->out_bytes = size_t(voxels) * P.nv4 * 16;
+        snprintf(pl->name, sizeof(pl->name), "%s", g_tiled[pl->inst].name);
+    } else {
+        pl->elem_bytes = (dtype == NDNLM_F64) ? 8 : 4;
+        pl->padded_bytes = size_t(pvox) * V * pl->elem_bytes;
+        pl->out_bytes = size_t(voxels) * V * pl->elem_bytes;
+        pl->threads = 256;
+        pl->grid = int(blocks_for(voxels, 256));
+        pl->smem = 0;
+        memset(P.g, 0, sizeof(P.g)); memset(P.t, 0, sizeof(P.t)); memset(P.b, 0, sizeof(P.b));
+        memset(P.tiles, 0, sizeof(P.tiles));
+        snprintf(pl->name, sizeof(pl->name), "nlm_generic<%s>%s", dtype == NDNLM_F64 ? "double" : "float",
+                 P.zero_dist ? "[zero_dist]" : "");
+    }
+    *out_plan = pl;
+    return NDNLM_OK;
+}
+
+extern "C" void ndnlm_plan_destroy(ndnlm_plan_t* plan) { delete plan; }
+
+extern "C" int ndnlm_plan_info(const ndnlm_plan_t* pl, ndnlm_info_t* info) {
+    if (!pl || !info) return fail(NDNLM_EINVAL, "null argument");
+    memset(info, 0, sizeof(*info));
+    info->kernel = pl->kernel;
+    for (int k = 0; k < 3; ++k) {
+        info->role_axis[k] = pl->perm[k];
+        info->n[k] = pl->P.n[k];
+        info->pad[k] = pl->P.pad[k];
+        info->padded[k] = pl->P.pd[k];
+        info->tile[k] = pl->P.t[k];
+        info->box[k] = pl->P.b[k];
+        info->warps[k] = pl->P.g[k];
+    }
+    info->vp = pl->kernel == NDNLM_KERNEL_TILED ? pl->P.nv4 * 4 : pl->P.V;
+    info->threads = pl->threads;
+    info->grid = pl->grid;
+    info->smem_bytes = int(pl->smem);
+    info->elem_bytes = pl->elem_bytes;
+    info->n_offsets = pl->n_offsets;
+    info->voxels = pl->shape[0] * pl->shape[1] * pl->shape[2];
+    info->flops_per_voxel = pl->flops_per_voxel;
+    info->padded_bytes = pl->padded_bytes;
+    info->out_bytes = pl->out_bytes;
+    snprintf(info->kernel_name, sizeof(info->kernel_name), "%s", pl->name);
+    return NDNLM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage / unstage / halo
+// ------------------------------------------------------------------------------------------
+static void fill_stage_params(const ndnlm_plan* pl, const int64_t strides[4], StageParams& S) {
+    for (int k = 0; k < 3; ++k) {
+        S.n[k] = pl->P.n[k];
+        S.pad[k] = pl->P.pad[k];
+        S.pd[k] = pl->P.pd[k];
+        S.rstride[k] = strides[pl->perm[k]];
+    }
+    S.vstride = strides[3];
+    S.V = pl->P.V;
+    S.nv4 = pl->P.nv4;
+    S.halo_role = -1;
+    S.lo_halo = S.hi_halo = 0;
+}
+
+static int role_of_axis(const ndnlm_plan* pl, int axis) {
+    for (int k = 0; k < 3; ++k)
+        if (pl->perm[k] == axis) return k;
+    return -1;
+}
+
+extern "C" int ndnlm_stage(const ndnlm_plan_t* pl, const void* arr, const int64_t arr_strides[4], void* padded,
+                           int shard_axis, int lo_edge, int hi_edge, void* stream) {
+    if (!pl || !arr || !arr_strides || !padded) return fail(NDNLM_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageParams S;
+    fill_stage_params(pl, arr_strides, S);
+    if (shard_axis >= 0) {
+        if (shard_axis > 2) return fail(NDNLM_EINVAL, "shard_axis must be -1..2");
+        S.halo_role = role_of_axis(pl, shard_axis);
+        S.lo_halo = lo_edge == NDNLM_EDGE_HALO;
+        S.hi_halo = hi_edge == NDNLM_EDGE_HALO;
+    }
+    const long long pvox = (long long)S.pd[0] * S.pd[1] * S.pd[2];
+    if (pl->kernel == NDNLM_KERNEL_TILED) {
+        const long long total = pvox * S.nv4;
+        stage_tiled_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(S, (const float*)arr, (float4*)padded);
+    } else if (pl->dtype == NDNLM_F64) {
+        const long long total = pvox * S.V;
+        stage_generic_kernel<double><<<blocks_for(total, 256), 256, 0, st>>>(S, (const double*)arr, (double*)padded);
+    } else {
+        const long long total = pvox * S.V;
+        stage_generic_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(S, (const float*)arr, (float*)padded);
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return NDNLM_OK;
+}
+
+extern "C" int ndnlm_unstage(const ndnlm_plan_t* pl, const void* internal, void* output, const int64_t out_strides[4],
+                             void* stream) {
+    if (!pl || !internal || !output || !out_strides) return fail(NDNLM_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    StageParams S;
+    fill_stage_params(pl, out_strides, S);
+    const long long vox = (long long)S.n[0] * S.n[1] * S.n[2];
+    if (pl->kernel == NDNLM_KERNEL_TILED) {
+        unstage_tiled_kernel<float><<<blocks_for(vox * S.nv4, 256), 256, 0, st>>>(S, (const float4*)internal, (float*)output);
+    } else if (pl->dtype == NDNLM_F64) {
+        unstage_generic_kernel<double><<<blocks_for(vox * S.V, 256), 256, 0, st>>>(S, (const double*)internal, (double*)output);
+    } else {
+        unstage_generic_kernel<float><<<blocks_for(vox * S.V, 256), 256, 0, st>>>(S, (const float*)internal, (float*)output);
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return NDNLM_OK;
+}
+
+// The padded cube as [outer][pd_hr][inner] in units of `unit` bytes.
+static void halo_geometry(const ndnlm_plan* pl, int role, long long& outer, long long& inner, int& unit) {
+    const DevParams& P = pl->P;
+    if (pl->kernel == NDNLM_KERNEL_TILED) {
+        unit = 16;
+        outer = P.nv4;
+        inner = 1;
+    } else {
+        unit = pl->elem_bytes;
+        outer = 1;
+        inner = P.V;
+    }
+    for (int k = 0; k < role; ++k) outer *= P.pd[k];
+    for (int k = role + 1; k < 3; ++k) inner *= P.pd[k];
+}
+
+extern "C" size_t ndnlm_halo_bytes(const ndnlm_plan_t* pl, int axis) {
+    if (!pl || axis < 0 || axis > 2) return 0;
+    const int role = role_of_axis(pl, axis);
+    long long outer, inner;
+    int unit;
+    halo_geometry(pl, role, outer, inner, unit);
+    return size_t(outer) * size_t(pl->P.pad[role]) * size_t(inner) * size_t(unit);
+}
+
+template <bool PACK>
+static int halo_copy(const ndnlm_plan* pl, void* padded, int axis, int side, void* msg, cudaStream_t st) {
+    if (!pl || !padded || !msg) return fail(NDNLM_EINVAL, "null argument");
+    if (axis < 0 || axis > 2 || side < 0 || side > 1) return fail(NDNLM_EINVAL, "bad axis/side");
+    const int role = role_of_axis(pl, axis);
+    const DevParams& P = pl->P;
+    const long long rows = P.pad[role];
+    if (rows == 0) return NDNLM_OK;
+    if (P.n[role] < rows) return fail(NDNLM_EINVAL, "shard has fewer interior rows (%d) than the halo (%lld)", P.n[role], rows);
+    long long outer, inner;
+    int unit;
+    halo_geometry(pl, role, outer, inner, unit);
+    long long first;
+    if (PACK) first = side == 0 ? rows : P.n[role];          // my first / last `pad` interior rows
+    else      first = side == 0 ? 0 : rows + P.n[role];      // my lower / upper pad rows
+    const long long total = outer * rows * inner;
+    if (unit == 16)
+        halo_copy_kernel<float4, PACK><<<blocks_for(total, 256), 256, 0, st>>>((float4*)padded, (float4*)msg, outer, P.pd[role], inner, first, rows);
+    else if (unit == 8)
+        halo_copy_kernel<double, PACK><<<blocks_for(total, 256), 256, 0, st>>>((double*)padded, (double*)msg, outer, P.pd[role], inner, first, rows);
+    else
+        halo_copy_kernel<float, PACK><<<blocks_for(total, 256), 256, 0, st>>>((float*)padded, (float*)msg, outer, P.pd[role], inner, first, rows);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return NDNLM_OK;
+}
+
+extern "C" int ndnlm_halo_pack(const ndnlm_plan_t* pl, const void* padded, int axis, int side, void* msg, void* stream) {
+    return halo_copy<true>(pl, const_cast<void*>(padded), axis, side, msg, (cudaStream_t)stream);
+}
+extern "C" int ndnlm_halo_unpack(const ndnlm_plan_t* pl, void* padded, int axis, int side, const void* msg, void* stream) {
+    return halo_copy<false>(pl, padded, axis, side, const_cast<void*>(msg), (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// run
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn() {
+    static encode_tiled_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    });
+    return fn;
+}
+
+extern "C" int ndnlm_run(const ndnlm_plan_t* pl, const void* padded, void* out_internal, int32_t* err_flag, void* stream) {
+    if (!pl || !padded || !out_internal || !err_flag) return fail(NDNLM_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevParams& P = pl->P;
+    if (pl->kernel == NDNLM_KERNEL_TILED) {
+        const TiledInst& ti = g_tiled[pl->inst];
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        if (!P.use_ldg_loader) {
+            encode_tiled_fn enc = get_encode_fn();
+            if (!enc) return fail(NDNLM_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+            // padded cube as a 5-D float tensor (v, x, r, w, q), innermost first
+            const cuuint64_t gdim[5] = {4, (cuuint64_t)P.pd[2], (cuuint64_t)P.pd[1], (cuuint64_t)P.pd[0], (cuuint64_t)P.nv4};
+            const cuuint64_t gstr[4] = {16, (cuuint64_t)P.pd[2] * 16, (cuuint64_t)P.pd[2] * P.pd[1] * 16,
+                                        (cuuint64_t)P.pd[2] * P.pd[1] * P.pd[0] * 16};
+            const cuuint32_t box[5] = {4, (cuuint32_t)P.b[2], (cuuint32_t)P.b[1], (cuuint32_t)P.b[0], 1};
+            const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(padded), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) return fail(NDNLM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(cr));
+        }
+        cudaError_t e = ti.launch(tmap, P, (const float4*)padded, (float4*)out_internal, err_flag, pl->grid, pl->smem, st);
+        g_launches++;
+        if (e != cudaSuccess) return fail(NDNLM_ECUDA, "tiled kernel launch failed: %s", cudaGetErrorString(e));
+    } else if (pl->dtype == NDNLM_F64) {
+        nlm_generic_kernel<double><<<pl->grid, 256, 0, st>>>(P, (const double*)padded, (double*)out_internal, err_flag);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        nlm_generic_kernel<float><<<pl->grid, 256, 0, st>>>(P, (const float*)padded, (float*)out_internal, err_flag);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return NDNLM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one-call apply
+// ------------------------------------------------------------------------------------------
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+extern "C" size_t ndnlm_workspace_bytes(const ndnlm_plan_t* pl) {
+    if (!pl) return 0;
+    return align256(pl->padded_bytes) + align256(pl->out_bytes) + 256;
+}
+
+extern "C" int ndnlm_apply(const ndnlm_plan_t* pl, const void* arr, const int64_t arr_strides[4], void* output,
+                           const int64_t out_strides[4], void* workspace, void* stream) {
+    if (!pl || !workspace) return fail(NDNLM_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    void* padded = ws;
+    void* internal = ws + align256(pl->padded_bytes);
+    int32_t* flag = (int32_t*)(ws + align256(pl->padded_bytes) + align256(pl->out_bytes));
+    CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+    int rc = ndnlm_stage(pl, arr, arr_strides, padded, -1, NDNLM_EDGE_REFLECT, NDNLM_EDGE_REFLECT, stream);
+    if (rc) return rc;
+    rc = ndnlm_run(pl, padded, internal, flag, stream);
+    if (rc) return rc;
+    rc = ndnlm_unstage(pl, internal, output, out_strides, stream);
+    if (rc) return rc;
+    int32_t hflag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&hflag, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (hflag) return fail(NDNLM_ENOSOLUTION, "No solution");
+    return NDNLM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic data, misc
+// ------------------------------------------------------------------------------------------
+extern "C" int ndnlm_synth_cube(float* out, int64_t ny_local, int64_t nx, int64_t nt, int32_t V, int64_t y_offset,
+                                uint64_t seed, void* stream) {
+    if (!out || ny_local < 1 || nx < 1 || nt < 1 || V < 1) return fail(NDNLM_EINVAL, "bad argument");
+    const long long total = (long long)ny_local * nx * nt;
+    synth_cube_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(out, ny_local, nx, nt, V, y_offset, seed);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return NDNLM_OK;
+}
+
+extern "C" int64_t ndnlm_launch_count(void) { return g_launches.load(); }
+extern "C" const char* ndnlm_last_error(void) { return g_err; }
+extern "C" const char* ndnlm_version(void) { return "ndnlm 0.1 (sm_100a)"; }

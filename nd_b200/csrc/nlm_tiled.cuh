@@ -1,0 +1,381 @@
+// nlm_tiled.cuh -- the TMA-tiled fp32 non-local-means kernel for sm_100a.
+//
+// Replaces the voxel / search-window / patch loops of the reference
+// (nd/_filters.pyx:351-420) for float32 data.  One CTA owns a (TW, TR, TX) tile of voxels:
+//
+//   * the reflect-padded input box (tile + halo r+f per axis) is brought into shared memory
+//     by ONE TMA tensor copy per variable group (cp.async.bulk.tensor.5d, mbarrier completion);
+//   * a warp is one W row x 32 X positions; a thread owns a column of L voxels along R
+//     (centre values, the neighbour window and all accumulators live in registers);
+//   * per search offset t: pointwise squared differences over the variables (packed
+//     FADD2/FMUL2/FFMA2), then a separable box sum over the patch: along R in registers,
+//     along X by warp shuffles, along W through a shared-memory exchange between warps;
+//     all sums are DIRECT (2f+1)-term sums in a fixed order, so a voxel's result does not
+//     depend on where its tile or shard starts;
+//   * weight w = exp2(-max(D*c1 - c2, 0)) (one FFMA, one NaN-propagating max, one MUFU.EX2),
+//     then acc += w * neighbour (FFMA2), S += w, M = max(M, w) [, Q += w*w];
+//   * weight sums are folded into float64 once per W-offset row (fp64-accumulated weight sums).
+//
+// No tensor cores: the path is not a dense contraction.  The binding unit is the FP32 pipe
+// (128 lane-ops/clk/SM, profiles/r1_pipe_microbench.txt).
+#pragma once
+#include "nlm_common.cuh"
+
+namespace ndnlm {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "NDNLM_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra NDNLM_DONE;\n"
+        "bra NDNLM_WAIT;\n"
+        "NDNLM_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// One 5-D TMA tile load: coordinates (v, x, r, w, q) in elements of the padded cube.
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+// max that PROPAGATES NaN, like the reference's `0 > x ? 0 : x` (nd/_filters.c:3604-3609).
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
+// Direct (2F+1)-term sum along the register column, fixed order.
+template <int F, int L>
+__device__ __forceinline__ void column_box_sum(const float (&s)[L + 2 * F], float (&o)[L]) {
+    if constexpr (F == 0) {
+#pragma unroll
+        for (int i = 0; i < L; ++i) o[i] = s[i];
+    } else if constexpr (F == 1) {
+#pragma unroll
+        for (int i = 0; i < L; ++i) o[i] = (s[i] + s[i + 1]) + s[i + 2];
+    } else if constexpr (F == 2) {
+        float a[L + 3];
+#pragma unroll
+        for (int i = 0; i < L + 3; ++i) a[i] = s[i] + s[i + 1];
+#pragma unroll
+        for (int i = 0; i < L; ++i) o[i] = (a[i] + a[i + 2]) + s[i + 4];
+    } else {
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+            float t = s[i];
+#pragma unroll
+            for (int d = 1; d <= 2 * F; ++d) t += s[i + d];
+            o[i] = t;
+        }
+    }
+}
+
+// Direct (2F+1)-term sum across lanes, fixed order (lane x gets x-F..x+F).
+template <int F>
+__device__ __forceinline__ float lane_box_sum(float v) {
+    if constexpr (F == 0) {
+        return v;
+    } else if constexpr (F == 1) {
+        const float a = __shfl_up_sync(FULL, v, 1);
+        const float b = __shfl_down_sync(FULL, v, 1);
+        return (a + v) + b;
+    } else {
+        float t = v;
+#pragma unroll
+        for (int d = 1; d <= F; ++d) {
+            const float a = __shfl_up_sync(FULL, v, d);
+            const float b = __shfl_down_sync(FULL, v, d);
+            t += a + b;
+        }
+        return t;
+    }
+}
+
+template <int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
+struct TiledCfg {
+    static constexpr int E = L + 2 * FR;      // column elements including the patch halo
+    static constexpr int WN = E + CH - 1;     // neighbour window elements per chunk of CH R-offsets
+    static constexpr int TXW = 32 - 2 * FX;   // valid lanes per warp
+    static constexpr int THREADS = NWARPS * 32;
+    static constexpr size_t EXCH_BYTES = FW > 0 ? size_t(CH) * NWARPS * (L / 2) * 32 * sizeof(float2) : 0;
+};
+
+template <int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
+                 const float4* __restrict__ padded, float4* __restrict__ out, int* __restrict__ err) {
+    using Cfg = TiledCfg<NV4, FW, FX, FR, L, NWARPS, CH, NEFF>;
+    static_assert(L % 2 == 0, "L must be even (outputs are exchanged in pairs)");
+    constexpr int E = Cfg::E, WN = Cfg::WN, TXW = Cfg::TXW;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int BW = P.b[0], BR = P.b[1], BX = P.b[2];
+    const int plane = ((BW * BR * BX + 7) >> 3) << 3;   // float4 per variable group, 128-B multiple
+    float4* tile = reinterpret_cast<float4*>(smem_raw);
+    float2* exch = reinterpret_cast<float2*>(smem_raw + size_t(NV4) * plane * sizeof(float4));
+    uint64_t* mbar =
+        reinterpret_cast<uint64_t*>(smem_raw + size_t(NV4) * plane * sizeof(float4) + Cfg::EXCH_BYTES);
+
+    int bid = blockIdx.x;
+    const int tileX = bid % P.tiles[2];
+    bid /= P.tiles[2];
+    const int tileR = bid % P.tiles[1];
+    const int tileW = bid / P.tiles[1];
+    const int w0 = tileW * P.t[0], r0 = tileR * P.t[1], x0 = tileX * P.t[2];
+
+    // ---- stage the padded box (tile + halo r+f) into shared memory ----
+    if (!P.use_ldg_loader) {
+        if (threadIdx.x == 0) {
+            mbar_init(mbar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(mbar, uint32_t(NV4) * uint32_t(BW * BR * BX) * 16u);
+#pragma unroll
+            for (int q = 0; q < NV4; ++q) tma_load_5d(tile + size_t(q) * plane, &tmap, mbar, 0, x0, r0, w0, q);
+        }
+        mbar_wait(mbar, 0);
+    } else {
+        const int box = BW * BR * BX;
+        for (int i = threadIdx.x; i < NV4 * box; i += blockDim.x) {
+            const int q = i / box;
+            int rem = i - q * box;
+            const int bx = rem % BX;
+            rem /= BX;
+            const int br = rem % BR;
+            const int bw = rem / BR;
+            const int gw = w0 + bw, gr = r0 + br, gx = x0 + bx;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gw < P.pd[0] && gr < P.pd[1] && gx < P.pd[2])
+                v = padded[((size_t(q) * P.pd[0] + gw) * P.pd[1] + gr) * P.pd[2] + gx];
+            tile[size_t(q) * plane + (bw * BR + br) * BX + bx] = v;
+        }
+        __syncthreads();
+    }
+
+    // ---- warp / lane roles ----
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gxw = P.g[2], grw = P.g[1];
+    const int wx = wid % gxw;
+    const int wr = (wid / gxw) % grw;
+    const int ww = wid / (gxw * grw);
+    const int wrow = gxw * grw;                 // warps per W row
+    const int lw = ww + P.rad[0];               // box coordinates of the centre column
+    const int lx = wx * TXW + lane + P.rad[2];
+    const int lr0 = wr * L + P.rad[1];
+    const bool wvalid = (FW == 0) || (ww >= FW && ww < P.g[0] - FW);
+
+    float4 c[NV4][E];
+#pragma unroll
+    for (int q = 0; q < NV4; ++q)
+#pragma unroll
+        for (int e = 0; e < E; ++e) c[q][e] = tile[size_t(q) * plane + (lw * BR + lr0 + e) * BX + lx];
+
+    float2 acc_lo[NV4][L], acc_hi[NV4][L];
+    float S[L], M[L], Q[L];
+    double Sd[L], Qd[L];
+#pragma unroll
+    for (int o = 0; o < L; ++o) {
+#pragma unroll
+        for (int q = 0; q < NV4; ++q) {
+            acc_lo[q][o] = make_float2(0.f, 0.f);
+            acc_hi[q][o] = make_float2(0.f, 0.f);
+        }
+        S[o] = 0.f;
+        M[o] = 0.f;
+        Q[o] = 0.f;
+        Sd[o] = 0.0;
+        Qd[o] = 0.0;
+    }
+
+    const int rW = P.rad[0], rR = P.rad[1], rX = P.rad[2];
+    const float2 c1 = make_float2(P.c1, P.c1);
+    const float2 nc2 = make_float2(-P.c2, -P.c2);
+
+    for (int tw = -rW; tw <= rW; ++tw) {
+        for (int tx = -rX; tx <= rX; ++tx) {
+            const float4* nb = tile + ((lw + tw) * BR + lr0) * BX + lx + tx;
+            for (int ch0 = -rR; ch0 <= rR; ch0 += CH) {
+                const int jmax = min(CH - 1, rR - ch0);   // last R-offset of this chunk (uniform)
+                const bool centre_step = (tw == 0) & (tx == 0);
+
+                // neighbour window: column elements e=0..E-1 shifted by R-offsets ch0..ch0+jmax
+                float4 n[NV4][WN];
+#pragma unroll
+                for (int k = 0; k < WN; ++k) {
+                    if (k <= E - 1 + jmax) {
+#pragma unroll
+                        for (int q = 0; q < NV4; ++q) n[q][k] = nb[size_t(q) * plane + (ch0 + k) * BX];
+                    }
+                }
+
+                // Weight + accumulate for the L outputs of R-offset j given patch sums D.
+                auto weigh = [&](const float2 (&D)[L / 2], const int j) {
+#pragma unroll
+                    for (int o2 = 0; o2 < L / 2; ++o2) {
+                        const float2 t = __ffma2_rn(D[o2], c1, nc2);
+                        const float w0_ = ex2_approx(-fmax_nan(t.x, 0.f));
+                        const float w1_ = ex2_approx(-fmax_nan(t.y, 0.f));
+                        const int o = 2 * o2;
+                        S[o] += w0_;
+                        S[o + 1] += w1_;
+                        M[o] = fmaxf(M[o], w0_);
+                        M[o + 1] = fmaxf(M[o + 1], w1_);
+                        if constexpr (NEFF) {
+                            Q[o] = fmaf(w0_, w0_, Q[o]);
+                            Q[o + 1] = fmaf(w1_, w1_, Q[o + 1]);
+                        }
+                        const float2 w0b = make_float2(w0_, w0_), w1b = make_float2(w1_, w1_);
+#pragma unroll
+                        for (int q = 0; q < NV4; ++q) {
+                            acc_lo[q][o] = __ffma2_rn(w0b, lo2(n[q][o + FR + j]), acc_lo[q][o]);
+                            acc_hi[q][o] = __ffma2_rn(w0b, hi2(n[q][o + FR + j]), acc_hi[q][o]);
+                            acc_lo[q][o + 1] = __ffma2_rn(w1b, lo2(n[q][o + 1 + FR + j]), acc_lo[q][o + 1]);
+                            acc_hi[q][o + 1] = __ffma2_rn(w1b, hi2(n[q][o + 1 + FR + j]), acc_hi[q][o + 1]);
+                        }
+                    }
+                };
+
+                // ---- phase A: squared differences, box sums along R (registers) and X (shuffles) ----
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    if (j > jmax) break;
+                    if (centre_step && (ch0 + j == 0)) continue;   // p == q is excluded (nd/_filters.pyx:368-369)
+                    float s[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        float2 sq;
+#pragma unroll
+                        for (int q = 0; q < NV4; ++q) {
+                            const float2 nlo = lo2(n[q][e + j]), nhi = hi2(n[q][e + j]);
+                            const float2 d0 = __fadd2_rn(lo2(c[q][e]), make_float2(-nlo.x, -nlo.y));
+                            const float2 d1 = __fadd2_rn(hi2(c[q][e]), make_float2(-nhi.x, -nhi.y));
+                            sq = (q == 0) ? __fmul2_rn(d0, d0) : __ffma2_rn(d0, d0, sq);
+                            sq = __ffma2_rn(d1, d1, sq);
+                        }
+                        s[e] = sq.x + sq.y;
+                    }
+                    float pr[L];
+                    column_box_sum<FR, L>(s, pr);
+                    float2 px[L / 2];
+#pragma unroll
+                    for (int o2 = 0; o2 < L / 2; ++o2) {
+                        px[o2].x = lane_box_sum<FX>(pr[2 * o2]);
+                        px[o2].y = lane_box_sum<FX>(pr[2 * o2 + 1]);
+                    }
+                    if constexpr (FW > 0) {
+#pragma unroll
+                        for (int o2 = 0; o2 < L / 2; ++o2)
+                            exch[((j * NWARPS + wid) * (L / 2) + o2) * 32 + lane] = px[o2];
+                    } else {
+                        weigh(px, j);
+                    }
+                }
+
+                // ---- phase B: box sum along W through shared memory, then weights ----
+                if constexpr (FW > 0) {
+                    __syncthreads();
+                    if (wvalid) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            if (j > jmax) break;
+                            if (centre_step && (ch0 + j == 0)) continue;
+                            float2 D[L / 2];
+#pragma unroll
+                            for (int o2 = 0; o2 < L / 2; ++o2) {
+                                float2 t = exch[((j * NWARPS + (wid - FW * wrow)) * (L / 2) + o2) * 32 + lane];
+#pragma unroll
+                                for (int d = -FW + 1; d <= FW; ++d) {
+                                    const float2 u =
+                                        exch[((j * NWARPS + (wid + d * wrow)) * (L / 2) + o2) * 32 + lane];
+                                    t = __fadd2_rn(t, u);
+                                }
+                                D[o2] = t;
+                            }
+                            weigh(D, j);
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        // fold the fp32 partial weight sums of this W-offset row into float64
+#pragma unroll
+        for (int o = 0; o < L; ++o) {
+            Sd[o] += double(S[o]);
+            S[o] = 0.f;
+            if constexpr (NEFF) {
+                Qd[o] += double(Q[o]);
+                Q[o] = 0.f;
+            }
+        }
+    }
+
+    // ---- epilogue: self weight, normalise, store (nd/_filters.pyx:405-420) ----
+    const int gw_ = w0 + ww - FW;
+    const int gx_ = x0 + wx * TXW + lane - FX;
+    if (wvalid && lane >= FX && lane < 32 - FX && gw_ < P.n[0] && gx_ < P.n[2]) {
+#pragma unroll
+        for (int o = 0; o < L; ++o) {
+            const int gr_ = r0 + wr * L + o;
+            if (gr_ >= P.n[1]) continue;
+            double ws;
+            if constexpr (NEFF) {
+                const double n_ = P.n_eff, Sx = Sd[o], Qx = Qd[o];
+                if (n_ - 1.0 > Sx * Sx / Qx) atomicExch(err, 1);   // find_weight: 'No solution' (:310-311)
+                ws = (Sx + sqrt(n_ * Sx * Sx - n_ * n_ * Qx + n_ * Qx)) / (n_ - 1.0);
+            } else {
+                ws = (M[o] == 0.f) ? 1.0 : double(M[o]);
+            }
+            const double tot = Sd[o] + ws;
+#pragma unroll
+            for (int q = 0; q < NV4; ++q) {
+                const float4 cc = c[q][o + FR];
+                float4 res;
+                // weighted_sum is float32 in the reference and is rounded after the self term (:419)
+                res.x = float(double(float(double(acc_lo[q][o].x) + ws * double(cc.x))) / tot);
+                res.y = float(double(float(double(acc_lo[q][o].y) + ws * double(cc.y))) / tot);
+                res.z = float(double(float(double(acc_hi[q][o].x) + ws * double(cc.z))) / tot);
+                res.w = float(double(float(double(acc_hi[q][o].y) + ws * double(cc.w))) / tot);
+                out[((size_t(q) * P.n[0] + gw_) * P.n[1] + gr_) * P.n[2] + gx_] = res;
+            }
+        }
+    }
+}
+
+}  // namespace ndnlm
