@@ -149,6 +149,12 @@ int ndnlm_apply(const ndnlm_plan_t* plan, const void* arr, const int64_t arr_str
 int ndnlm_synth_cube(float* out, int64_t ny_local, int64_t nx, int64_t nt, int32_t V,
                      int64_t y_offset, uint64_t seed, void* stream);
 
+/*
+ * FP32 FMA-chain microbenchmark on the current device (runs for about `seconds`): the measured
+ * CUDA-core peak in TFLOP/s, reported by bench.py beside the nominal SMs*128*2*clock roofline.
+ */
+int ndnlm_measure_fp32_peak(double* tflops, double seconds, void* stream);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t ndnlm_launch_count(void);
 

@@ -33,7 +33,7 @@ def _as_u32_3(x, name):
 
 
 def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=None, kernel='auto',
-                          njobs=1, shard_axis=None):
+                          njobs=1, shard_axis=None, devices=None):
     """
     GPU replacement of `nd._filters._pixelwise_nlmeans_3d` (reference nd/_filters.pyx:320-420).
 
@@ -44,6 +44,8 @@ def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=No
     semantics   : 'as_written' (default) or 'reference_compiled' (SURVEY.md D1); also ND_NLM_SEMANTICS.
     njobs       : number of GPUs to shard over along `shard_axis` (default: the largest axis that is
                   not filtered, else the largest axis -- reference nd/filters.py:424-435).
+    devices     : optional explicit CUDA device index per shard (e.g. [0, 0] exercises the shard /
+                  halo-exchange layer on a single GPU).
     """
     import torch
     from . import device as dev
@@ -70,8 +72,10 @@ def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=No
     njobs = int(njobs)
     if njobs == -1:
         njobs = torch.cuda.device_count()
-    if njobs > 1:
-        _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis)
+    if devices is not None:
+        njobs = len(devices)
+    if njobs > 1 or devices is not None:
+        _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis, devices)
         return
 
     plan = dev.Plan(arr.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)
@@ -89,15 +93,18 @@ def _copy_back(output, d_out):
         output[...] = d_out.cpu().numpy()
 
 
-def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis):
+def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis, devices=None):
     """Single-process multi-GPU apply: shard along one axis, halo rows over NVLink peer copies."""
     import torch
     from . import device as dev
     from .shard import ShardPlan, exchange_halos_p2p
 
     ndev = torch.cuda.device_count()
-    if njobs > ndev:
-        raise ValueError('njobs=%d but only %d CUDA devices are visible' % (njobs, ndev))
+    if devices is None:
+        if njobs > ndev:
+            raise ValueError('njobs=%d but only %d CUDA devices are visible' % (njobs, ndev))
+        devices = list(range(njobs))
+    devices = [int(d) for d in devices]
     if shard_axis is None:
         free = [a for a in range(3) if r3[a] == 0 and f3[a] == 0]
         cand = free if free else [0, 1, 2]
@@ -109,16 +116,16 @@ def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, sha
         idx = [slice(None)] * 4
         idx[shard_axis] = slice(lo, hi)
         slab = arr[tuple(idx)]
-        with torch.cuda.device(i):
+        with torch.cuda.device(devices[i]):
             plan = dev.Plan(slab.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)
-            d_in = torch.from_numpy(slab).to('cuda:%d' % i, non_blocking=True)
+            d_in = torch.from_numpy(slab).to('cuda:%d' % devices[i], non_blocking=True)
             padded = plan.new_padded(d_in.device)
             lo_e, hi_e = sp.edges(i)
             plan.stage(d_in, padded, shard_axis, lo_e, hi_e)
         plans.append(plan); paddeds.append(padded); slabs.append((idx, d_in))
     exchange_halos_p2p(plans, paddeds, shard_axis)
     for i, plan in enumerate(plans):
-        with torch.cuda.device(i):
+        with torch.cuda.device(devices[i]):
             internal = plan.new_internal_out(paddeds[i].device)
             flag = torch.zeros(1, dtype=torch.int32, device=paddeds[i].device)
             plan.run(paddeds[i], internal, flag)
@@ -127,7 +134,7 @@ def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, sha
         outs.append(d_out); flags.append(flag)
     bad = False
     for i, d_out in enumerate(outs):
-        torch.cuda.synchronize(i)
+        torch.cuda.synchronize(devices[i])
         bad = bad or bool(flags[i].item())
         output[tuple(slabs[i][0])] = d_out.cpu().numpy()
     if bad:

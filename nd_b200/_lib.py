@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libndnlm.so")
+LIB_PATH = os.environ.get("NDNLM_LIB") or os.path.join(_HERE, "libndnlm.so")   # NDNLM_LIB: tuning builds only
 
 OK, EINVAL, EDTYPE, ECUDA, ENOSOLUTION, ERADIUS = 0, -1, -2, -3, -4, -5
 F32, F64 = 0, 1
@@ -24,7 +24,7 @@ KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "tiled": KERNEL_TILED
 SYMBOLS = [
     "ndnlm_plan_create", "ndnlm_plan_destroy", "ndnlm_plan_info", "ndnlm_stage", "ndnlm_halo_bytes",
     "ndnlm_halo_pack", "ndnlm_halo_unpack", "ndnlm_run", "ndnlm_unstage", "ndnlm_workspace_bytes",
-    "ndnlm_apply", "ndnlm_synth_cube", "ndnlm_launch_count", "ndnlm_last_error", "ndnlm_version",
+    "ndnlm_apply", "ndnlm_synth_cube", "ndnlm_measure_fp32_peak", "ndnlm_launch_count", "ndnlm_last_error", "ndnlm_version",
 ]
 
 
@@ -92,6 +92,8 @@ def lib():
     L.ndnlm_synth_cube.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                    ctypes.c_int64, ctypes.c_uint64, vp]
     L.ndnlm_synth_cube.restype = ctypes.c_int
+    L.ndnlm_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_double, vp]
+    L.ndnlm_measure_fp32_peak.restype = ctypes.c_int
     L.ndnlm_launch_count.argtypes = []
     L.ndnlm_launch_count.restype = ctypes.c_int64
     L.ndnlm_last_error.argtypes = []

@@ -136,6 +136,7 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti) {
     if (P.t[0] < 1) return false;
     P.b[0] = gw + 2 * P.rad[0];
     P.b[1] = gr * ti.L + 2 * ti.fr + 2 * P.rad[1];
+    P.b[1] |= 1;   // odd R pitch in shared memory: conflict-free LDS.128 across lanes (R is the fastest axis)
     P.b[2] = gx * txw + 2 * ti.fx + 2 * P.rad[2];
     for (int k = 0; k < 3; ++k)
         if (P.b[k] > 256) return false;
@@ -146,7 +147,7 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti) {
     }
     if (tiles > 0x7fffffffLL) return false;
     const size_t plane = ((size_t(P.b[0]) * P.b[1] * P.b[2] + 7) / 8) * 8;
-    const size_t smem = size_t(ti.nv4) * plane * 16 + ti.exch_bytes + 16;
+    const size_t smem = size_t(ti.nv4) * plane * 16 + ti.exch_bytes + 16 + 16 * size_t(ti.nwarps);
     if (smem > kMaxSmem) return false;
     pl->smem = smem;
     pl->threads = ti.nwarps * 32;
@@ -380,17 +381,25 @@ extern "C" int ndnlm_unstage(const ndnlm_plan_t* pl, const void* internal, void*
 // The padded cube as [outer][pd_hr][inner] in units of `unit` bytes.
 static void halo_geometry(const ndnlm_plan* pl, int role, long long& outer, long long& inner, int& unit) {
     const DevParams& P = pl->P;
+    // memory order of the roles, slowest first: tiled [q][W][X][R], generic [W][R][X][V]
+    const int tiled_order[3] = {ROLE_W, ROLE_X, ROLE_R};
+    const int generic_order[3] = {ROLE_W, ROLE_R, ROLE_X};
+    const int* order;
     if (pl->kernel == NDNLM_KERNEL_TILED) {
         unit = 16;
         outer = P.nv4;
         inner = 1;
+        order = tiled_order;
     } else {
         unit = pl->elem_bytes;
         outer = 1;
         inner = P.V;
+        order = generic_order;
     }
-    for (int k = 0; k < role; ++k) outer *= P.pd[k];
-    for (int k = role + 1; k < 3; ++k) inner *= P.pd[k];
+    int pos = 0;
+    while (order[pos] != role) ++pos;
+    for (int k = 0; k < pos; ++k) outer *= P.pd[order[k]];
+    for (int k = pos + 1; k < 3; ++k) inner *= P.pd[order[k]];
 }
 
 extern "C" size_t ndnlm_halo_bytes(const ndnlm_plan_t* pl, int axis) {
@@ -467,11 +476,11 @@ extern "C" int ndnlm_run(const ndnlm_plan_t* pl, const void* padded, void* out_i
         if (!P.use_ldg_loader) {
             encode_tiled_fn enc = get_encode_fn();
             if (!enc) return fail(NDNLM_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-            // padded cube as a 5-D float tensor (v, x, r, w, q), innermost first
-            const cuuint64_t gdim[5] = {4, (cuuint64_t)P.pd[2], (cuuint64_t)P.pd[1], (cuuint64_t)P.pd[0], (cuuint64_t)P.nv4};
-            const cuuint64_t gstr[4] = {16, (cuuint64_t)P.pd[2] * 16, (cuuint64_t)P.pd[2] * P.pd[1] * 16,
-                                        (cuuint64_t)P.pd[2] * P.pd[1] * P.pd[0] * 16};
-            const cuuint32_t box[5] = {4, (cuuint32_t)P.b[2], (cuuint32_t)P.b[1], (cuuint32_t)P.b[0], 1};
+            // padded cube [q][W][X][R] as a 5-D float tensor (v, r, x, w, q), innermost first
+            const cuuint64_t gdim[5] = {4, (cuuint64_t)P.pd[1], (cuuint64_t)P.pd[2], (cuuint64_t)P.pd[0], (cuuint64_t)P.nv4};
+            const cuuint64_t gstr[4] = {16, (cuuint64_t)P.pd[1] * 16, (cuuint64_t)P.pd[1] * P.pd[2] * 16,
+                                        (cuuint64_t)P.pd[1] * P.pd[2] * P.pd[0] * 16};
+            const cuuint32_t box[5] = {4, (cuuint32_t)P.b[1], (cuuint32_t)P.b[2], (cuuint32_t)P.b[0], 1};
             const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
             CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(padded), gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -535,6 +544,54 @@ extern "C" int ndnlm_synth_cube(float* out, int64_t ny_local, int64_t nx, int64_
     synth_cube_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(out, ny_local, nx, nt, V, y_offset, seed);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    return NDNLM_OK;
+}
+
+// FP32 FMA-chain microbenchmark: the measured CUDA-core peak of THIS device under load, the
+// denominator beside the nominal SMs*128*2*clock figure.
+__global__ void __launch_bounds__(1024) fp32_peak_kernel(float* out, float a, float b, int iters) {
+    float r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = threadIdx.x * 0.001f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = fmaf(r[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int ndnlm_measure_fp32_peak(double* tflops, double seconds, void* stream) {
+    if (!tflops) return fail(NDNLM_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, sizeof(float) * size_t(sms) * 2 * 1024));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 1 << 15;
+    double best = 0.0, elapsed = 0.0;
+    for (int rep = 0; rep < 1000 && (rep < 3 || elapsed < seconds); ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, st));
+        fp32_peak_kernel<<<sms * 2, 1024, 0, st>>>(out, 1.0001f, 0.5f, iters);
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 16.0 * double(iters) * double(sms) * 2.0 * 1024.0;
+        if (rep > 0 && fl / (ms * 1e-3) > best) best = fl / (ms * 1e-3);
+        elapsed += ms * 1e-3;
+        g_launches++;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best * 1e-12;
     return NDNLM_OK;
 }
 

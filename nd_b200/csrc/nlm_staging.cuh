@@ -8,7 +8,7 @@
 //   synth    counter-based synthetic SAR-like cube keyed by GLOBAL voxel index.
 //
 // Two internal layouts:
-//   tiled    [nv4][W][R][X] float4  (variables padded with zeros to a multiple of 4)
+//   tiled    [nv4][W][X][R] float4  (R fastest; variables padded with zeros to a multiple of 4)
 //   generic  [W][R][X][V]   T
 #pragma once
 #include "nlm_common.cuh"
@@ -31,11 +31,11 @@ __global__ void stage_tiled_kernel(const StageParams S, const TIN* __restrict__ 
     if (i >= plane * S.nv4) return;
     const int q = int(i / plane);
     long long rem = i - q * plane;
-    int ip[3];
-    ip[2] = int(rem % S.pd[2]);
-    rem /= S.pd[2];
+    int ip[3];                       // tiled layout: R fastest, then X, then W
     ip[1] = int(rem % S.pd[1]);
-    ip[0] = int(rem / S.pd[1]);
+    rem /= S.pd[1];
+    ip[2] = int(rem % S.pd[2]);
+    ip[0] = int(rem / S.pd[2]);
     long long src = 0;
 #pragma unroll
     for (int role = 0; role < 3; ++role) {
@@ -87,11 +87,11 @@ __global__ void unstage_tiled_kernel(const StageParams S, const float4* __restri
     if (i >= plane * S.nv4) return;
     const int q = int(i / plane);
     long long rem = i - q * plane;
-    int ip[3];
-    ip[2] = int(rem % S.n[2]);
-    rem /= S.n[2];
+    int ip[3];                       // tiled layout: R fastest, then X, then W
     ip[1] = int(rem % S.n[1]);
-    ip[0] = int(rem / S.n[1]);
+    rem /= S.n[1];
+    ip[2] = int(rem % S.n[2]);
+    ip[0] = int(rem / S.n[2]);
     long long dst = 0;
 #pragma unroll
     for (int role = 0; role < 3; ++role) dst += (long long)ip[role] * S.rstride[role];

@@ -19,11 +19,17 @@
 // No tensor cores: the path is not a dense contraction.  The binding unit is the FP32 pipe
 // (128 lane-ops/clk/SM, profiles/r1_pipe_microbench.txt).
 #pragma once
+#include <type_traits>
+
 #include "nlm_common.cuh"
+
+#ifndef NDNLM_FOLD_T
+#define NDNLM_FOLD_T double   // type of the second-level weight-sum accumulators
+#endif
 
 namespace ndnlm {
 
-constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned FULL_MASK = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -41,6 +47,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -54,7 +63,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// One 5-D TMA tile load: coordinates (v, x, r, w, q) in elements of the padded cube.
+// One 5-D TMA tile load: coordinates (v, r, x, w, q) in elements of the padded cube.
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             int c2, int c3, int c4) {
     asm volatile(
@@ -110,18 +119,31 @@ __device__ __forceinline__ float lane_box_sum(float v) {
     if constexpr (F == 0) {
         return v;
     } else if constexpr (F == 1) {
-        const float a = __shfl_up_sync(FULL, v, 1);
-        const float b = __shfl_down_sync(FULL, v, 1);
+        const float a = __shfl_up_sync(FULL_MASK, v, 1);
+        const float b = __shfl_down_sync(FULL_MASK, v, 1);
         return (a + v) + b;
     } else {
         float t = v;
 #pragma unroll
         for (int d = 1; d <= F; ++d) {
-            const float a = __shfl_up_sync(FULL, v, d);
-            const float b = __shfl_down_sync(FULL, v, d);
+            const float a = __shfl_up_sync(FULL_MASK, v, d);
+            const float b = __shfl_down_sync(FULL_MASK, v, d);
             t += a + b;
         }
         return t;
+    }
+}
+
+// Call fn(integral_constant<int, nj>, bool_constant<centre>) for the runtime (uniform) nj in 1..MAXJ.
+template <int MAXJ, typename Fn>
+__device__ __forceinline__ void dispatch_chunk(const int nj, const bool centre, Fn&& fn) {
+    if constexpr (MAXJ >= 1) {
+        if (nj == MAXJ) {
+            if (centre) fn(std::integral_constant<int, MAXJ>{}, std::true_type{});
+            else        fn(std::integral_constant<int, MAXJ>{}, std::false_type{});
+        } else {
+            dispatch_chunk<MAXJ - 1>(nj, centre, fn);
+        }
     }
 }
 
@@ -142,13 +164,21 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     static_assert(L % 2 == 0, "L must be even (outputs are exchanged in pairs)");
     constexpr int E = Cfg::E, WN = Cfg::WN, TXW = Cfg::TXW;
 
+    // Shared memory: the padded box as [q][BW][BX][BRP] float4 -- R is the FASTEST axis and its
+    // pitch BRP is odd, so a thread's column / neighbour window is a run of consecutive float4
+    // (immediate LDS offsets) and the 8 lanes of an LDS.128 phase hit 8 distinct 16-B bank groups.
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int BW = P.b[0], BR = P.b[1], BX = P.b[2];
-    const int plane = ((BW * BR * BX + 7) >> 3) << 3;   // float4 per variable group, 128-B multiple
+    const int BW = P.b[0], BRP = P.b[1], BX = P.b[2];
+    const int plane = ((BW * BRP * BX + 7) >> 3) << 3;   // float4 per variable group, 128-B multiple
     float4* tile = reinterpret_cast<float4*>(smem_raw);
     float2* exch = reinterpret_cast<float2*>(smem_raw + size_t(NV4) * plane * sizeof(float4));
     uint64_t* mbar =
         reinterpret_cast<uint64_t*>(smem_raw + size_t(NV4) * plane * sizeof(float4) + Cfg::EXCH_BYTES);
+    // Neighbour-only synchronisation of the W exchange (no CTA-wide barrier in the hot loop):
+    //   full[w]   warp w's patch sums for the current chunk are in shared memory        (1 arrival)
+    //   empty[w]  every warp that reads warp w's sums has finished with them             (nreaders arrivals)
+    uint64_t* mbar_full = mbar + 1;
+    uint64_t* mbar_empty = mbar + 1 + NWARPS;
 
     int bid = blockIdx.x;
     const int tileX = bid % P.tiles[2];
@@ -158,57 +188,68 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     const int w0 = tileW * P.t[0], r0 = tileR * P.t[1], x0 = tileX * P.t[2];
 
     // ---- stage the padded box (tile + halo r+f) into shared memory ----
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        if constexpr (FW > 0) {
+            for (int w = 0; w < NWARPS; ++w) {
+                int readers = 0;   // valid warps within FW rows of w, other than w itself
+                for (int d = -FW; d <= FW; ++d)
+                    if (d != 0 && w + d >= FW && w + d < NWARPS - FW) ++readers;
+                mbar_init(mbar_full + w, 1);
+                mbar_init(mbar_empty + w, readers > 0 ? readers : 1);
+            }
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
     if (!P.use_ldg_loader) {
         if (threadIdx.x == 0) {
-            mbar_init(mbar, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(mbar, uint32_t(NV4) * uint32_t(BW * BR * BX) * 16u);
+            mbar_arrive_expect_tx(mbar, uint32_t(NV4) * uint32_t(BW * BRP * BX) * 16u);
 #pragma unroll
-            for (int q = 0; q < NV4; ++q) tma_load_5d(tile + size_t(q) * plane, &tmap, mbar, 0, x0, r0, w0, q);
+            for (int q = 0; q < NV4; ++q) tma_load_5d(tile + size_t(q) * plane, &tmap, mbar, 0, r0, x0, w0, q);
         }
         mbar_wait(mbar, 0);
     } else {
-        const int box = BW * BR * BX;
+        const int box = BW * BRP * BX;
         for (int i = threadIdx.x; i < NV4 * box; i += blockDim.x) {
             const int q = i / box;
             int rem = i - q * box;
+            const int br = rem % BRP;
+            rem /= BRP;
             const int bx = rem % BX;
-            rem /= BX;
-            const int br = rem % BR;
-            const int bw = rem / BR;
+            const int bw = rem / BX;
             const int gw = w0 + bw, gr = r0 + br, gx = x0 + bx;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gw < P.pd[0] && gr < P.pd[1] && gx < P.pd[2])
-                v = padded[((size_t(q) * P.pd[0] + gw) * P.pd[1] + gr) * P.pd[2] + gx];
-            tile[size_t(q) * plane + (bw * BR + br) * BX + bx] = v;
+                v = padded[((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr];
+            tile[size_t(q) * plane + (bw * BX + bx) * BRP + br] = v;
         }
         __syncthreads();
     }
 
     // ---- warp / lane roles ----
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gxw = P.g[2], grw = P.g[1];
+    const int gxw = (FW > 0) ? 1 : P.g[2], grw = (FW > 0) ? 1 : P.g[1];
     const int wx = wid % gxw;
     const int wr = (wid / gxw) % grw;
     const int ww = wid / (gxw * grw);
-    const int wrow = gxw * grw;                 // warps per W row
     const int lw = ww + P.rad[0];               // box coordinates of the centre column
     const int lx = wx * TXW + lane + P.rad[2];
     const int lr0 = wr * L + P.rad[1];
-    const bool wvalid = (FW == 0) || (ww >= FW && ww < P.g[0] - FW);
+    const bool wvalid = (FW == 0) || (ww >= FW && ww < NWARPS - FW);
 
     float4 c[NV4][E];
+    {
+        const float4* pc = tile + (lw * BX + lx) * BRP + lr0;
 #pragma unroll
-    for (int q = 0; q < NV4; ++q)
+        for (int q = 0; q < NV4; ++q)
 #pragma unroll
-        for (int e = 0; e < E; ++e) c[q][e] = tile[size_t(q) * plane + (lw * BR + lr0 + e) * BX + lx];
+            for (int e = 0; e < E; ++e) c[q][e] = pc[size_t(q) * plane + e];
+    }
 
     float2 acc_lo[NV4][L], acc_hi[NV4][L];
     float S[L], M[L], Q[L];
-    double Sd[L], Qd[L];
+    NDNLM_FOLD_T Sd[L], Qd[L];
 #pragma unroll
     for (int o = 0; o < L; ++o) {
 #pragma unroll
@@ -219,128 +260,162 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         S[o] = 0.f;
         M[o] = 0.f;
         Q[o] = 0.f;
-        Sd[o] = 0.0;
-        Qd[o] = 0.0;
+        Sd[o] = 0;
+        Qd[o] = 0;
     }
 
     const int rW = P.rad[0], rR = P.rad[1], rX = P.rad[2];
     const float2 c1 = make_float2(P.c1, P.c1);
     const float2 nc2 = make_float2(-P.c2, -P.c2);
+    float2* const ex_own = exch + (wid * (L / 2)) * 32 + lane;     // + (j*NWARPS*(L/2) + o2)*32
+    constexpr int EX_J = NWARPS * (L / 2) * 32;                     // float2 stride between R-offsets j
+    constexpr int EX_ROW = (L / 2) * 32;                            // float2 stride between W rows (FW>0: 1 warp/row)
+    uint32_t xpar = 0;                                              // parity of the current exchange round
+    bool first_publish = true;
+    int nreaders = 0;
+    if constexpr (FW > 0) {
+#pragma unroll
+        for (int d = -FW; d <= FW; ++d)
+            if (d != 0 && wid + d >= FW && wid + d < NWARPS - FW) ++nreaders;
+    }
+
+    // One chunk of NJ consecutive R-offsets [ch0, ch0+NJ).  NJ is a compile-time constant so the body is
+    // straight-line code the scheduler can interleave freely.  CENTRE: the chunk contains the centre
+    // voxel itself (tw = tx = 0 and ch0 <= 0 < ch0+NJ), whose offset must be skipped -- rare slow path.
+    auto chunk = [&](auto nj_tag, auto centre_tag, const float4* nb, const int ch0) {
+        constexpr int NJ = decltype(nj_tag)::value;
+        constexpr bool CENTRE = decltype(centre_tag)::value;
+        constexpr int WNJ = E + NJ - 1;
+        bool waited = false;
+
+        float4 n[NV4][WNJ];
+#pragma unroll
+        for (int k = 0; k < WNJ; ++k) {
+#pragma unroll
+            for (int q = 0; q < NV4; ++q) n[q][k] = nb[size_t(q) * plane + k];
+        }
+
+        auto weigh = [&](const float2 (&D)[L / 2], const int j) {
+#pragma unroll
+            for (int o2 = 0; o2 < L / 2; ++o2) {
+                const float2 t = __ffma2_rn(D[o2], c1, nc2);
+                const float w0_ = ex2_approx(-fmax_nan(t.x, 0.f));
+                const float w1_ = ex2_approx(-fmax_nan(t.y, 0.f));
+                const int o = 2 * o2;
+                S[o] += w0_;
+                S[o + 1] += w1_;
+                M[o] = fmaxf(M[o], w0_);
+                M[o + 1] = fmaxf(M[o + 1], w1_);
+                if constexpr (NEFF) {
+                    Q[o] = fmaf(w0_, w0_, Q[o]);
+                    Q[o + 1] = fmaf(w1_, w1_, Q[o + 1]);
+                }
+                const float2 w0b = make_float2(w0_, w0_), w1b = make_float2(w1_, w1_);
+#pragma unroll
+                for (int q = 0; q < NV4; ++q) {
+                    acc_lo[q][o] = __ffma2_rn(w0b, lo2(n[q][o + FR + j]), acc_lo[q][o]);
+                    acc_hi[q][o] = __ffma2_rn(w0b, hi2(n[q][o + FR + j]), acc_hi[q][o]);
+                    acc_lo[q][o + 1] = __ffma2_rn(w1b, lo2(n[q][o + 1 + FR + j]), acc_lo[q][o + 1]);
+                    acc_hi[q][o + 1] = __ffma2_rn(w1b, hi2(n[q][o + 1 + FR + j]), acc_hi[q][o + 1]);
+                }
+            }
+        };
+
+        // ---- phase A: squared differences, box sums along R (registers) and X (shuffles) ----
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if constexpr (CENTRE) {
+                if (ch0 + j == 0) continue;   // p == q is excluded (nd/_filters.pyx:368-369)
+            }
+            float s[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                float2 sq;
+#pragma unroll
+                for (int q = 0; q < NV4; ++q) {
+                    const float2 nlo = lo2(n[q][e + j]), nhi = hi2(n[q][e + j]);
+                    const float2 d0 = __fadd2_rn(lo2(c[q][e]), make_float2(-nlo.x, -nlo.y));
+                    const float2 d1 = __fadd2_rn(hi2(c[q][e]), make_float2(-nhi.x, -nhi.y));
+                    sq = (q == 0) ? __fmul2_rn(d0, d0) : __ffma2_rn(d0, d0, sq);
+                    sq = __ffma2_rn(d1, d1, sq);
+                }
+                s[e] = sq.x + sq.y;
+            }
+            float pr[L];
+            column_box_sum<FR, L>(s, pr);
+            float2 px[L / 2];
+#pragma unroll
+            for (int o2 = 0; o2 < L / 2; ++o2) {
+                px[o2].x = lane_box_sum<FX>(pr[2 * o2]);
+                px[o2].y = lane_box_sum<FX>(pr[2 * o2 + 1]);
+            }
+            if constexpr (FW == 0) {
+                weigh(px, j);
+            } else {
+                // before the first store of this chunk: my readers must be done with the previous round
+                if (!waited) {
+                    if (!first_publish && nreaders > 0) mbar_wait(mbar_empty + wid, xpar ^ 1);
+                    first_publish = false;
+                    waited = true;
+                }
+#pragma unroll
+                for (int o2 = 0; o2 < L / 2; ++o2) ex_own[j * EX_J + o2 * 32] = px[o2];
+            }
+        }
+
+        // ---- phase B: box sum along W through shared memory, then weights ----
+        if constexpr (FW > 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(mbar_full + wid);          // release: my sums are published
+            if (wvalid) {
+#pragma unroll
+                for (int d = -FW; d <= FW; ++d)
+                    if (d != 0) mbar_wait(mbar_full + wid + d, xpar);   // acquire the neighbour rows
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    if constexpr (CENTRE) {
+                        if (ch0 + j == 0) continue;
+                    }
+                    float2 D[L / 2];
+#pragma unroll
+                    for (int o2 = 0; o2 < L / 2; ++o2) {
+                        float2 t = ex_own[j * EX_J + o2 * 32 - FW * EX_ROW];
+#pragma unroll
+                        for (int d = -FW + 1; d <= FW; ++d) t = __fadd2_rn(t, ex_own[j * EX_J + o2 * 32 + d * EX_ROW]);
+                        D[o2] = t;
+                    }
+                    weigh(D, j);
+                }
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int d = -FW; d <= FW; ++d)
+                        if (d != 0) mbar_arrive(mbar_empty + wid + d);   // done reading the neighbour rows
+                }
+            }
+            xpar ^= 1;
+        }
+    };
 
     for (int tw = -rW; tw <= rW; ++tw) {
         for (int tx = -rX; tx <= rX; ++tx) {
-            const float4* nb = tile + ((lw + tw) * BR + lr0) * BX + lx + tx;
+            const float4* nb0 = tile + ((lw + tw) * BX + lx + tx) * BRP + lr0;
+            const bool centre_step = (tw == 0) & (tx == 0);
             for (int ch0 = -rR; ch0 <= rR; ch0 += CH) {
-                const int jmax = min(CH - 1, rR - ch0);   // last R-offset of this chunk (uniform)
-                const bool centre_step = (tw == 0) & (tx == 0);
-
-                // neighbour window: column elements e=0..E-1 shifted by R-offsets ch0..ch0+jmax
-                float4 n[NV4][WN];
-#pragma unroll
-                for (int k = 0; k < WN; ++k) {
-                    if (k <= E - 1 + jmax) {
-#pragma unroll
-                        for (int q = 0; q < NV4; ++q) n[q][k] = nb[size_t(q) * plane + (ch0 + k) * BX];
-                    }
-                }
-
-                // Weight + accumulate for the L outputs of R-offset j given patch sums D.
-                auto weigh = [&](const float2 (&D)[L / 2], const int j) {
-#pragma unroll
-                    for (int o2 = 0; o2 < L / 2; ++o2) {
-                        const float2 t = __ffma2_rn(D[o2], c1, nc2);
-                        const float w0_ = ex2_approx(-fmax_nan(t.x, 0.f));
-                        const float w1_ = ex2_approx(-fmax_nan(t.y, 0.f));
-                        const int o = 2 * o2;
-                        S[o] += w0_;
-                        S[o + 1] += w1_;
-                        M[o] = fmaxf(M[o], w0_);
-                        M[o + 1] = fmaxf(M[o + 1], w1_);
-                        if constexpr (NEFF) {
-                            Q[o] = fmaf(w0_, w0_, Q[o]);
-                            Q[o + 1] = fmaf(w1_, w1_, Q[o + 1]);
-                        }
-                        const float2 w0b = make_float2(w0_, w0_), w1b = make_float2(w1_, w1_);
-#pragma unroll
-                        for (int q = 0; q < NV4; ++q) {
-                            acc_lo[q][o] = __ffma2_rn(w0b, lo2(n[q][o + FR + j]), acc_lo[q][o]);
-                            acc_hi[q][o] = __ffma2_rn(w0b, hi2(n[q][o + FR + j]), acc_hi[q][o]);
-                            acc_lo[q][o + 1] = __ffma2_rn(w1b, lo2(n[q][o + 1 + FR + j]), acc_lo[q][o + 1]);
-                            acc_hi[q][o + 1] = __ffma2_rn(w1b, hi2(n[q][o + 1 + FR + j]), acc_hi[q][o + 1]);
-                        }
-                    }
-                };
-
-                // ---- phase A: squared differences, box sums along R (registers) and X (shuffles) ----
-#pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    if (j > jmax) break;
-                    if (centre_step && (ch0 + j == 0)) continue;   // p == q is excluded (nd/_filters.pyx:368-369)
-                    float s[E];
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        float2 sq;
-#pragma unroll
-                        for (int q = 0; q < NV4; ++q) {
-                            const float2 nlo = lo2(n[q][e + j]), nhi = hi2(n[q][e + j]);
-                            const float2 d0 = __fadd2_rn(lo2(c[q][e]), make_float2(-nlo.x, -nlo.y));
-                            const float2 d1 = __fadd2_rn(hi2(c[q][e]), make_float2(-nhi.x, -nhi.y));
-                            sq = (q == 0) ? __fmul2_rn(d0, d0) : __ffma2_rn(d0, d0, sq);
-                            sq = __ffma2_rn(d1, d1, sq);
-                        }
-                        s[e] = sq.x + sq.y;
-                    }
-                    float pr[L];
-                    column_box_sum<FR, L>(s, pr);
-                    float2 px[L / 2];
-#pragma unroll
-                    for (int o2 = 0; o2 < L / 2; ++o2) {
-                        px[o2].x = lane_box_sum<FX>(pr[2 * o2]);
-                        px[o2].y = lane_box_sum<FX>(pr[2 * o2 + 1]);
-                    }
-                    if constexpr (FW > 0) {
-#pragma unroll
-                        for (int o2 = 0; o2 < L / 2; ++o2)
-                            exch[((j * NWARPS + wid) * (L / 2) + o2) * 32 + lane] = px[o2];
-                    } else {
-                        weigh(px, j);
-                    }
-                }
-
-                // ---- phase B: box sum along W through shared memory, then weights ----
-                if constexpr (FW > 0) {
-                    __syncthreads();
-                    if (wvalid) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) {
-                            if (j > jmax) break;
-                            if (centre_step && (ch0 + j == 0)) continue;
-                            float2 D[L / 2];
-#pragma unroll
-                            for (int o2 = 0; o2 < L / 2; ++o2) {
-                                float2 t = exch[((j * NWARPS + (wid - FW * wrow)) * (L / 2) + o2) * 32 + lane];
-#pragma unroll
-                                for (int d = -FW + 1; d <= FW; ++d) {
-                                    const float2 u =
-                                        exch[((j * NWARPS + (wid + d * wrow)) * (L / 2) + o2) * 32 + lane];
-                                    t = __fadd2_rn(t, u);
-                                }
-                                D[o2] = t;
-                            }
-                            weigh(D, j);
-                        }
-                    }
-                    __syncthreads();
-                }
+                const int nj = min(CH, rR - ch0 + 1);                        // uniform
+                const bool centre = centre_step && ch0 <= 0 && ch0 + nj > 0;
+                dispatch_chunk<CH>(nj, centre, [&](auto nj_tag, auto centre_tag) {
+                    chunk(nj_tag, centre_tag, nb0 + ch0, ch0);
+                });
             }
         }
         // fold the fp32 partial weight sums of this W-offset row into float64
 #pragma unroll
         for (int o = 0; o < L; ++o) {
-            Sd[o] += double(S[o]);
+            Sd[o] += NDNLM_FOLD_T(S[o]);
             S[o] = 0.f;
             if constexpr (NEFF) {
-                Qd[o] += double(Q[o]);
+                Qd[o] += NDNLM_FOLD_T(Q[o]);
                 Q[o] = 0.f;
             }
         }
@@ -350,19 +425,21 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     const int gw_ = w0 + ww - FW;
     const int gx_ = x0 + wx * TXW + lane - FX;
     if (wvalid && lane >= FX && lane < 32 - FX && gw_ < P.n[0] && gx_ < P.n[2]) {
+        float4* po = out + (size_t(gw_) * P.n[2] + gx_) * P.n[1] + (r0 + wr * L);   // out is [q][W][X][R]
+        const size_t oplane = size_t(P.n[0]) * P.n[1] * P.n[2];
 #pragma unroll
         for (int o = 0; o < L; ++o) {
             const int gr_ = r0 + wr * L + o;
             if (gr_ >= P.n[1]) continue;
             double ws;
             if constexpr (NEFF) {
-                const double n_ = P.n_eff, Sx = Sd[o], Qx = Qd[o];
+                const double n_ = P.n_eff, Sx = double(Sd[o]), Qx = double(Qd[o]);
                 if (n_ - 1.0 > Sx * Sx / Qx) atomicExch(err, 1);   // find_weight: 'No solution' (:310-311)
                 ws = (Sx + sqrt(n_ * Sx * Sx - n_ * n_ * Qx + n_ * Qx)) / (n_ - 1.0);
             } else {
                 ws = (M[o] == 0.f) ? 1.0 : double(M[o]);
             }
-            const double tot = Sd[o] + ws;
+            const double tot = double(Sd[o]) + ws;
 #pragma unroll
             for (int q = 0; q < NV4; ++q) {
                 const float4 cc = c[q][o + FR];
@@ -372,7 +449,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 res.y = float(double(float(double(acc_lo[q][o].y) + ws * double(cc.y))) / tot);
                 res.z = float(double(float(double(acc_hi[q][o].x) + ws * double(cc.z))) / tot);
                 res.w = float(double(float(double(acc_hi[q][o].y) + ws * double(cc.w))) / tot);
-                out[((size_t(q) * P.n[0] + gw_) * P.n[1] + gr_) * P.n[2] + gx_] = res;
+                po[q * oplane + o] = res;
             }
         }
     }

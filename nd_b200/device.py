@@ -144,5 +144,13 @@ def synth_cube(ny_local, nx, nt, V=4, y_offset=0, seed=42, device="cuda"):
     return out
 
 
+def measure_fp32_peak(seconds=0.5):
+    """Measured FP32 FMA peak of the current device in TFLOP/s (ndnlm_measure_fp32_peak)."""
+    v = ctypes.c_double(0.0)
+    _lib.check(_lib.lib().ndnlm_measure_fp32_peak(ctypes.byref(v), float(seconds),
+                                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return float(v.value)
+
+
 def launch_count():
     return int(_lib.lib().ndnlm_launch_count())

@@ -1,0 +1,241 @@
+"""
+`Filter` / `NLMeansFilter`, mirroring reference nd/filters.py:82-198 and :388-466.
+
+Same public surface: `NLMeansFilter(dims, r, sigma, h, f, n_eff).apply(ds, inplace=False, njobs=1)`
+takes and returns a Dataset with the same dims, coords and attrs; the filter plugs in through
+`Filter._filter(self, arr, axes, output)` (signature pinned by the reference's
+nd/tests/test_filters_common.py:37-41).  Below that boundary the reference calls its Cython kernel;
+here `_filter` calls `nd_b200._filters._pixelwise_nlmeans_3d`, which runs on the GPU.
+
+Datasets: anything with the small xarray subset used here (`data_vars`, `ds[name].dims/.values`,
+`copy(deep=True)`, item assignment / deletion): real `xarray.Dataset`s when xarray is installed,
+`nd_b200.dataset.Dataset` otherwise (xarray is absent in this image).
+"""
+import re
+from abc import abstractmethod
+
+import numpy as np
+
+from .algorithm import Algorithm, parallelize, wrap_algorithm
+from ._filters import _pixelwise_nlmeans_3d
+
+
+# ---- helpers restated from nd/utils.py:450-524 and nd/io.py:26-123 ---------------------------
+def _is_dataarray(ds):
+    return hasattr(ds, 'values') and hasattr(ds, 'dims') and not hasattr(ds, 'data_vars')
+
+
+def get_vars_for_dims(ds, dims, invert=False):
+    """All variables of `ds` whose dims contain `dims` (reference nd/utils.py:450-469)."""
+    return [v for v in ds.data_vars if set(ds[v].dims).issuperset(set(dims)) != invert]
+
+
+def is_complex(ds):
+    """reference nd/utils.py:502-524"""
+    if _is_dataarray(ds):
+        return np.iscomplexobj(ds.values)
+    return bool(np.any([np.iscomplexobj(ds[v].values) for v in ds.data_vars]))
+
+
+def disassemble_complex(ds):
+    """Split complex variables into `__re` / `__im` in place (reference nd/io.py:26-69)."""
+    for vn in list(ds.data_vars):
+        var = ds[vn]
+        if not np.iscomplexobj(var.values):
+            continue
+        ds[vn + '__re'] = (var.dims, np.ascontiguousarray(var.values.real))
+        ds[vn + '__im'] = (var.dims, np.ascontiguousarray(var.values.imag))
+        del ds[vn]
+
+
+def assemble_complex(ds):
+    """Inverse of `disassemble_complex`, in place (reference nd/io.py:72-123)."""
+    names = list(ds.data_vars)
+    stems = {}
+    for vn in names:
+        m = re.match(r'(?P<stem>.*)(?:_real|__re)$', vn)
+        if m:
+            stems.setdefault(m.group('stem'), {})['re'] = vn
+        m = re.match(r'(?P<stem>.*)(?:_imag|__im)$', vn)
+        if m:
+            stems.setdefault(m.group('stem'), {})['im'] = vn
+    for stem, parts in stems.items():
+        if 're' in parts and 'im' in parts:
+            re_v, im_v = ds[parts['re']], ds[parts['im']]
+            ds[stem] = (re_v.dims, re_v.values + im_v.values * 1j)
+            del ds[parts['re']]
+            del ds[parts['im']]
+
+
+class Filter(Algorithm):
+    """
+    The base class for a generic filter (reference nd/filters.py:82-198).
+
+    Parameters
+    ----------
+    dims : tuple of str
+        The dimensions along which the filter is applied.
+    """
+
+    # If per_variable is True, the filter is applied independently for each variable.
+    per_variable = True
+    # If supports_complex is False, complex variables are split into two reals before filtering.
+    supports_complex = False
+    dims = ()
+
+    @abstractmethod
+    def __init__(self, *args, **kwargs):
+        return
+
+    @parallelize
+    def apply(self, ds, inplace=False):
+        """
+        Apply the filter to the input dataset.
+
+        Parameters
+        ----------
+        ds : xarray.Dataset
+            The input dataset
+        inplace : bool, optional
+            If True, overwrite the input data inplace (default: False).
+
+        Returns
+        -------
+        xarray.Dataset
+            The filtered dataset
+        """
+        if inplace:
+            raise NotImplementedError('Inplace filtering is not currently implemented.')
+
+        convert_complex = is_complex(ds) and not self.supports_complex
+        if convert_complex:
+            disassemble_complex(ds)
+
+        if _is_dataarray(ds):
+            # DataArray: the raw values go to the filter, whose last axis then plays "variables"
+            # (quirk of the reference preserved, nd/filters.py:139-145 + :447-463).
+            result = ds.copy(deep=True)
+            axes = tuple(list(result.dims).index(d) for d in self.dims)
+            self._filter(ds.values, axes, output=result.values)
+        else:
+            variables = get_vars_for_dims(ds, self.dims)
+            result = ds.copy(deep=True)
+            if self.per_variable:
+                for v in variables:
+                    vdims = result[v].dims
+                    axes = tuple(list(vdims).index(d) for d in self.dims)
+                    self._filter(ds[v].values, axes, output=result[v].values)
+            elif variables:
+                self._apply_joint(ds, result, variables)
+
+        if convert_complex:
+            assemble_complex(ds)
+        return result
+
+    def _apply_joint(self, ds, result, variables):
+        """per_variable=False: the variables are an extra trailing axis (nd/filters.py:164-185)."""
+        vdims = tuple(ds[variables[0]].dims)
+        for v in variables[1:]:
+            if set(ds[v].dims) != set(vdims):
+                raise ValueError('all filtered variables must share the same dimensions '
+                                 '(%r has %r, %r has %r)' % (variables[0], vdims, v, tuple(ds[v].dims)))
+        ordered_dims = tuple(self.dims) + tuple(d for d in vdims if d not in self.dims)
+        dtype = np.result_type(*[ds[v].values.dtype for v in variables])
+        shape = tuple(ds[variables[0]].values.shape[vdims.index(d)] for d in ordered_dims)
+        # variable-major block like `to_array()`; the (dims..., variable) view handed to `_filter`
+        # is a transposed view of it (nd/filters.py:170)
+        block = np.empty((len(variables),) + shape, dtype=dtype)
+        for i, v in enumerate(variables):
+            src = ds[v].values
+            perm = [list(ds[v].dims).index(d) for d in ordered_dims]
+            block[i] = np.transpose(src, perm)
+        out_block = block.copy()
+        arr = np.moveaxis(block, 0, -1)
+        out = np.moveaxis(out_block, 0, -1)
+        axes = tuple(ordered_dims.index(d) for d in self.dims)
+        self._filter(arr, axes, output=out)
+        for i, v in enumerate(variables):
+            dst_dims = list(result[v].dims)
+            perm = [ordered_dims.index(d) for d in dst_dims]
+            result[v].values[...] = np.transpose(out_block[i], perm)
+
+    @abstractmethod
+    def _filter(self, arr, axes, output=None):
+        """This method must be implemented by all derived classes."""
+        return
+
+
+class NLMeansFilter(Filter):
+    """
+    Non-Local Means (Buades2011), reference nd/filters.py:388-466.
+
+    Parameters
+    ----------
+    dims : tuple of str
+        The dataset dimensions along which to filter.
+    r : {int, sequence}
+        The radius
+    sigma : float
+        The standard deviation of the noise present in the data.
+    h : float
+    f : int
+    n_eff : float, optional
+        The desired effective sample size (-1: none, default).
+    semantics : {'as_written', 'reference_compiled'}, keyword-only, optional
+        Patch-distance semantics.  Default 'as_written' (or ND_NLM_SEMANTICS).
+    """
+
+    per_variable = False
+
+    def __init__(self, dims=('y', 'x'), r=1, sigma=1, h=1, f=1, n_eff=-1, *, semantics=None, kernel='auto'):
+        if isinstance(r, (int, float)):
+            r = [r] * len(dims)
+        self.dims = tuple(dims)
+        self.r = np.array(r, dtype=np.uint32)
+        self.f = np.array([f if _ > 0 else 0 for _ in self.r], dtype=np.uint32)
+        self.sigma = sigma
+        self.h = h
+        self.n_eff = n_eff
+        self.semantics = semantics
+        self.kernel = kernel
+        self._njobs = 1
+
+    def _parallel_dimension(self, ds):
+        """Largest non-filter dimension, else the largest dimension (nd/filters.py:424-435)."""
+        sizes = {}
+        for v in ds.data_vars:
+            for d, n in zip(ds[v].dims, ds[v].values.shape):
+                sizes[d] = n
+        extra = [d for d in sizes if d not in self.dims]
+        pool = extra if extra else list(sizes)
+        return sorted(pool, key=lambda d: sizes[d], reverse=True)[0]
+
+    def _buffer(self, dim):
+        """Halo needed when sharding over `dim`: r + f on that axis (nd/filters.py:437-445)."""
+        if dim not in self.dims:
+            return 0
+        axis = self.dims.index(dim)
+        return int(self.r[axis] + self.f[axis])
+
+    def _filter(self, arr, axes, output):
+        # Pad r and f to three dimensions (nd/filters.py:451-454); `axes` is ignored as in the reference.
+        pad_before = np.zeros(4 - arr.ndim, dtype=self.r.dtype)
+        pad_after = np.zeros(arr.ndim - len(self.r) - 1, dtype=self.r.dtype)
+        r = np.concatenate([pad_before, self.r, pad_after])
+        f = np.concatenate([pad_before, self.f, pad_after])
+        # Pad input and output to four dimensions (views, never copies) (nd/filters.py:459-460).
+        values = arr.reshape((1,) * (4 - arr.ndim) + arr.shape)
+        _out = output.reshape((1,) * (4 - output.ndim) + output.shape)
+        if not np.shares_memory(_out, output):
+            raise ValueError('output must be viewable as a 4-D array without copying')
+        if len(self.r) == 0 or not np.any(r):
+            # r == 0 everywhere: no neighbours, self weight 1 -> exact identity (nd/_filters.pyx:406-420;
+            # pinned exactly by nd/tests/test_nlmeans_filter.py:17-25).  Nothing to compute.
+            if self.n_eff < 0:
+                _out[...] = values
+                return
+        _pixelwise_nlmeans_3d(values, _out, r, f, self.sigma, self.h, self.n_eff,
+                              semantics=self.semantics, kernel=self.kernel, njobs=getattr(self, '_njobs', 1))
+
+
+nlmeans = wrap_algorithm(NLMeansFilter, 'nlmeans')

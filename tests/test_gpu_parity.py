@@ -1,0 +1,268 @@
+"""
+GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI
+(libndnlm.so via ctypes -- `nd_b200.device.Plan` / `nd_b200._filters._pixelwise_nlmeans_3d`), against
+  * the committed golden vectors = outputs of the reference's own compiled kernel (tests/golden/),
+  * the C oracle on seeded inputs (bit-exact twin of the reference, tests/test_oracle.py),
+  * size-independent properties at larger sizes (shard invariance, identity, box mean, loader equality).
+Tolerance: the north_star's max relative error <= 1e-4, measured per variable as
+max|out-ref| / max|ref_v|; float64 data must agree to 1e-12.
+Nothing here reads /root/reference.
+"""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+from helpers import sar_like, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-4       # north_star tolerance (fp32 compute)
+TOL64 = 1e-12
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    from nd_b200 import device
+    assert torch.cuda.is_available()
+    return device
+
+
+def run_plan(device, a, r, f, sigma, h, n_eff=-1, semantics="as_written", kernel="auto"):
+    import torch
+    plan = device.Plan(a.shape, r, f, sigma, h, n_eff, semantics=semantics, dtype=a.dtype, kernel=kernel)
+    out = plan.apply(torch.from_numpy(a).cuda())
+    return out.cpu().numpy(), plan
+
+
+# ---- golden vectors: outputs of the reference's own binary ---------------------------------------
+@pytest.mark.parametrize("semantics,key", [("as_written", "__out_as_written"), ("reference_compiled", "__out_compiled")])
+def test_golden_vectors(dev, golden, semantics, key):
+    z, meta = golden
+    launches0 = dev.launch_count()
+    for name, m in meta.items():
+        a = z[name + "__in"]
+        out, plan = run_plan(dev, a, m["r"], m["f"], m["sigma"], m["h"], m["n_eff"], semantics)
+        tol = TOL64 if a.dtype == np.float64 else TOL32
+        err = scaled_err(out, z[name + key])
+        assert err < tol, (name, semantics, plan.kernel_name, err)
+        assert out.dtype == a.dtype
+    assert dev.launch_count() > launches0           # the CUDA library really ran
+
+
+def test_golden_vectors_tiled_kernel_is_used_and_tight(dev, golden):
+    """float32 as-written cases with V<=4 must go through the TMA-tiled kernel and agree far better than 1e-4."""
+    z, meta = golden
+    for name in ("3d_f1_f32", "2d_f1_slc", "3d_f0_f32", "3d_batch_t", "1d_f1_V1"):
+        m = meta[name]
+        out, plan = run_plan(dev, z[name + "__in"], m["r"], m["f"], m["sigma"], m["h"], m["n_eff"], kernel="tiled")
+        assert plan.is_tiled
+        assert scaled_err(out, z[name + "__out_as_written"]) < 5e-6, name
+
+
+# ---- seeded inputs vs the C oracle ----------------------------------------------------------------
+CASES = [
+    # shape, r, f  (as-written, float32)
+    ((20, 45, 14, 4), (2, 3, 1), (1, 1, 1)),
+    ((30, 70, 16, 4), (5, 5, 2), (1, 1, 1)),       # cfg3 parameters
+    ((33, 61, 9, 4), (3, 3, 2), (1, 1, 1)),        # sizes that are not multiples of the tile
+    ((7, 7, 4, 4), (3, 3, 1), (1, 1, 1)),          # minimal extents: r+f = N-1 on two axes ... reflection at both ends
+    ((1, 40, 70, 4), (0, 3, 3), (0, 1, 1)),        # 2-D (cfg1 parameters)
+    ((20, 33, 5, 4), (2, 2, 0), (1, 1, 0)),        # time is a batch axis
+    ((6, 20, 15, 4), (1, 2, 1), (0, 0, 0)),        # f = 0
+    ((5, 6, 50, 2), (0, 0, 4), (0, 0, 1)),         # 1-D, V=2
+    ((14, 37, 8, 3), (1, 2, 2), (1, 1, 1)),        # V=3
+    ((14, 37, 8, 1), (1, 2, 2), (1, 1, 1)),        # V=1
+    ((12, 18, 9, 4), (2, 2, 1), (2, 2, 2)),        # f = 2
+    ((9, 12, 8, 6), (1, 1, 1), (1, 1, 1)),         # V=6 (cfg5 variable count)
+    ((8, 9, 7, 9), (1, 1, 1), (1, 1, 1)),          # V > 8: several passes of the generic kernel
+    ((10, 12, 6, 4), (0, 2, 0), (1, 1, 1)),        # patch axes that are not search axes (direct C-ABI use)
+]
+
+
+@pytest.mark.parametrize("shape,r,f", CASES)
+def test_matches_oracle_float32(dev, c_oracle, shape, r, f):
+    a = sar_like(shape, seed=sum(shape), dtype=np.float32)
+    ref = c_oracle.nlmeans(a, r, f, 0.3, 0.6)
+    out, plan = run_plan(dev, a, r, f, 0.3, 0.6)
+    assert scaled_err(out, ref) < TOL32, plan.kernel_name
+    assert not np.isnan(out).any()
+
+
+@pytest.mark.parametrize("shape,r,f", CASES[:3] + CASES[4:7])
+def test_generic_kernel_matches_oracle_closely(dev, c_oracle, shape, r, f):
+    """The generic kernel mirrors the reference's arithmetic (fp64 weights): agreement ~1e-6."""
+    a = sar_like(shape, seed=1 + sum(shape), dtype=np.float32)
+    ref = c_oracle.nlmeans(a, r, f, 0.3, 0.6)
+    out, plan = run_plan(dev, a, r, f, 0.3, 0.6, kernel="generic")
+    assert "generic" in plan.kernel_name and scaled_err(out, ref) < 3e-6
+
+
+@pytest.mark.parametrize("shape,r,f", [CASES[0], CASES[4], CASES[5], CASES[10]])
+def test_float64_matches_oracle(dev, c_oracle, shape, r, f):
+    a = sar_like(shape, seed=3, dtype=np.float64)
+    for sem in ("as_written", "reference_compiled"):
+        ref = c_oracle.nlmeans(a, r, f, 0.3, 0.6, semantics=sem)
+        out, plan = run_plan(dev, a, r, f, 0.3, 0.6, semantics=sem)
+        assert out.dtype == np.float64 and scaled_err(out, ref) < TOL64, (plan.kernel_name, sem)
+
+
+@pytest.mark.parametrize("shape,r,f", [CASES[0], CASES[4], CASES[10]])
+def test_reference_compiled_semantics(dev, c_oracle, shape, r, f):
+    a = sar_like(shape, seed=4, dtype=np.float32)
+    ref = c_oracle.nlmeans(a, r, f, 0.3, 0.6, semantics="reference_compiled")
+    out, plan = run_plan(dev, a, r, f, 0.3, 0.6, semantics="reference_compiled")
+    assert scaled_err(out, ref) < 3e-6, plan.kernel_name
+
+
+def test_neff(dev, c_oracle):
+    a = sar_like((10, 16, 7, 4), seed=5, dtype=np.float32)
+    for r, f in (((2, 2, 1), (1, 1, 1)), ((0, 2, 2), (0, 1, 1))):
+        ref = c_oracle.nlmeans(a, r, f, 0.3, 1.5, n_eff=6.0)
+        out, plan = run_plan(dev, a, r, f, 0.3, 1.5, n_eff=6.0)
+        assert scaled_err(out, ref) < TOL32, plan.kernel_name
+
+
+def test_neff_no_solution_raises_value_error(dev):
+    a = sar_like((8, 9, 6, 2), seed=6, dtype=np.float32)
+    with pytest.raises(ValueError, match="No solution"):      # nd/_filters.pyx:310-311
+        run_plan(dev, a, (1, 1, 1), (0, 0, 0), 0.01, 0.01, n_eff=20.0)
+
+
+def test_nan_footprint_matches_reference(dev, c_oracle):
+    a = sar_like((1, 15, 15, 3), seed=2, dtype=np.float32)
+    a[0, 7, 7, 0] = np.nan
+    for f, sem in (((0, 0, 0), "as_written"), ((0, 1, 1), "as_written"), ((0, 1, 1), "reference_compiled")):
+        ref = c_oracle.nlmeans(a, (0, 2, 2), f, 0.3, 0.6, semantics=sem)
+        out, plan = run_plan(dev, a, (0, 2, 2), f, 0.3, 0.6, semantics=sem)
+        assert np.array_equal(np.isnan(out), np.isnan(ref)), (plan.kernel_name, f, sem)
+        assert scaled_err(np.nan_to_num(out), np.nan_to_num(ref)) < TOL32
+
+
+def test_strided_variable_major_input(dev, c_oracle):
+    """What Filter.apply hands over: a (dims..., variable) VIEW of a variable-major block (nd/filters.py:170)."""
+    import torch
+    a = sar_like((12, 20, 8, 4), seed=7, dtype=np.float32)
+    block = np.ascontiguousarray(np.moveaxis(a, -1, 0))
+    view = np.moveaxis(block, 0, -1)
+    ref = c_oracle.nlmeans(a, (2, 2, 1), (1, 1, 1), 0.3, 0.6)
+    plan = dev.Plan(a.shape, (2, 2, 1), (1, 1, 1), 0.3, 0.6)
+    t = torch.from_numpy(view).cuda()
+    assert not t.is_contiguous()
+    out = torch.empty_like(t)
+    plan.apply(t, out)
+    assert out.stride() == t.stride()
+    assert scaled_err(out.cpu().numpy(), ref) < TOL32
+
+
+def test_tma_loader_equals_plain_loader_bitwise(dev):
+    a = sar_like((25, 64, 12, 4), seed=8, dtype=np.float32)
+    out_tma, plan = run_plan(dev, a, (3, 3, 2), (1, 1, 1), 0.3, 0.6, kernel="tiled")
+    os.environ["NDNLM_LOADER"] = "ldg"
+    try:
+        out_ldg, _ = run_plan(dev, a, (3, 3, 2), (1, 1, 1), 0.3, 0.6, kernel="tiled")
+    finally:
+        del os.environ["NDNLM_LOADER"]
+    assert np.array_equal(out_tma, out_ldg)
+
+
+# ---- properties at larger sizes --------------------------------------------------------------------
+def test_constant_cube_identity_and_huge_sigma_box_mean(dev):
+    a = np.full((40, 70, 10, 4), 2.5, dtype=np.float32)
+    out, _ = run_plan(dev, a, (3, 3, 2), (1, 1, 1), 0.1, 0.2)
+    assert np.array_equal(out, a)
+    b = sar_like((16, 40, 8, 4), seed=9, dtype=np.float32)
+    r = (2, 3, 1)
+    out, _ = run_plan(dev, b, r, (1, 1, 1), 1e3, 1.0)
+    P = np.pad(b.astype(np.float64), [(k, k) for k in r] + [(0, 0)], mode="reflect")
+    box = np.zeros(b.shape)
+    for t in itertools.product(*[range(2 * k + 1) for k in r]):
+        box += P[t[0]:t[0] + 16, t[1]:t[1] + 40, t[2]:t[2] + 8]
+    box /= np.prod([2 * k + 1 for k in r])
+    assert scaled_err(out, box) < 2e-6
+
+
+def test_deterministic(dev):
+    a = sar_like((64, 100, 32, 4), seed=10, dtype=np.float32)
+    o1, _ = run_plan(dev, a, (3, 3, 2), (1, 1, 1), 0.25, 0.5)
+    o2, _ = run_plan(dev, a, (3, 3, 2), (1, 1, 1), 0.25, 0.5)
+    assert np.array_equal(o1, o2)
+
+
+@pytest.mark.parametrize("nshards", [2, 3])
+def test_sharded_equals_unsharded_bitwise(dev, nshards):
+    """The halo layer on ONE GPU (devices=[0,0,..]): y-shards + neighbour halo rows == unsharded, bit for bit
+    (the reference's test_parallelized_filter, nd/tests/test_filters_common.py:54-60, asks rtol 1e-5)."""
+    from nd_b200._filters import _pixelwise_nlmeans_3d
+    a = sar_like((50, 64, 10, 4), seed=11, dtype=np.float32)
+    r, f = np.array([3, 3, 1], np.uint32), np.array([1, 1, 1], np.uint32)
+    whole = np.empty_like(a)
+    _pixelwise_nlmeans_3d(a, whole, r, f, 0.3, 0.6)
+    parts = np.empty_like(a)
+    _pixelwise_nlmeans_3d(a, parts, r, f, 0.3, 0.6, devices=[0] * nshards, shard_axis=0)
+    assert np.array_equal(whole, parts)
+    # sharding along a non-filtered axis needs no halo at all
+    r2, f2 = np.array([2, 2, 0], np.uint32), np.array([1, 1, 0], np.uint32)
+    _pixelwise_nlmeans_3d(a, whole, r2, f2, 0.3, 0.6)
+    _pixelwise_nlmeans_3d(a, parts, r2, f2, 0.3, 0.6, devices=[0] * nshards, shard_axis=2)
+    assert np.array_equal(whole, parts)
+
+
+def test_large_cube_sampled_against_oracle(dev, c_oracle):
+    """cfg3 parameters on a cube that is many tiles in every direction; sub-cubes (corner, edge, interior)
+    are checked against the oracle run on the same values (with halo r+f around the sample)."""
+    import torch
+    ny, nx, nt = 96, 256, 32
+    cube = dev.synth_cube(ny, nx, nt, 4)
+    r, f = (5, 5, 2), (1, 1, 1)
+    plan = dev.Plan(cube.shape, r, f, 0.25, 0.5)
+    out = plan.apply(cube).cpu().numpy()
+    a = cube.cpu().numpy()
+    assert plan.is_tiled and np.isfinite(out).all()
+    pad = (6, 6, 3)
+    for (y0, x0) in ((0, 0), (ny - 12, nx - 20), (40, 100), (0, 117)):
+        ys, xs = slice(max(y0 - pad[0], 0), min(y0 + 12 + pad[0], ny)), slice(max(x0 - pad[1], 0), min(x0 + 20 + pad[1], nx))
+        sub = np.ascontiguousarray(a[ys, xs])
+        ref = c_oracle.nlmeans(sub, r, f, 0.25, 0.5)
+        # voxels whose whole window lies inside `sub` (or is cut by a TRUE cube edge, where both reflect alike)
+        iy = slice(y0 - ys.start, y0 - ys.start + 12)
+        ix = slice(x0 - xs.start, x0 - xs.start + 20)
+        assert scaled_err(out[y0:y0 + 12, x0:x0 + 20], ref[iy, ix]) < TOL32, (y0, x0)
+
+
+# ---- the reference's own filter tests, through the Dataset API -------------------------------------
+def test_reference_filter_tests_through_dataset_api(dev):
+    from nd_b200.dataset import generate_test_dataset
+    from nd_b200.filters import NLMeansFilter, nlmeans
+    ds = generate_test_dataset(dims={'y': 20, 'x': 20, 'time': 10})
+    # nd/tests/test_nlmeans_filter.py:28-32 (reduce std)
+    ds_nlm = NLMeansFilter(dims=('y', 'x', 'time'), r=(1, 1, 0), sigma=2, h=2).apply(ds)
+    assert all(ds_nlm[v].values.std() < ds[v].values.std() for v in ds.data_vars)
+    assert ds_nlm.attrs == ds.attrs and all(ds_nlm[v].dims == ds[v].dims for v in ds.data_vars)
+    # :35-43 (r_time = 0 == per-slice 2-D call, to 1e-8)
+    t0 = ds.isel(time=0)
+    t0_nlm = NLMeansFilter(dims=('y', 'x'), r=1, sigma=2, h=2).apply(t0)
+    for v in ds.data_vars:
+        assert np.abs(ds_nlm.isel(time=0)[v].values - t0_nlm[v].values).max() < 1e-8
+    # nd/tests/test_filters_common.py:44-51 (dims order does not matter, rtol 1e-5)
+    a = NLMeansFilter(dims=('y', 'x')).apply(ds)
+    b = nlmeans(ds, dims=('x', 'y'))
+    for v in ds.data_vars:
+        assert np.allclose(a[v].values, b[v].values, rtol=1e-5, atol=1e-8)
+    # float32 Dataset goes through the tiled kernel and returns float32
+    ds32 = generate_test_dataset(dims={'y': 24, 'x': 40, 'time': 6}, dtype=np.float32)
+    out32 = NLMeansFilter(dims=('y', 'x', 'time'), r=(2, 2, 1), sigma=0.5, h=1.0).apply(ds32)
+    assert all(out32[v].values.dtype == np.float32 for v in ds32.data_vars)
+
+
+def test_complex_variables_are_split_and_reassembled(dev):
+    from nd_b200.dataset import Dataset
+    from nd_b200.filters import NLMeansFilter
+    rng = np.random.default_rng(0)
+    ds = Dataset({'C12': (('y', 'x'), (rng.normal(size=(12, 14)) + 1j * rng.normal(size=(12, 14)))),
+                  'C11': (('y', 'x'), rng.gamma(4, 0.25, size=(12, 14)))}, coords={'y': np.arange(12), 'x': np.arange(14)})
+    out = NLMeansFilter(dims=('y', 'x'), r=1, sigma=1, h=1).apply(ds)
+    assert 'C12' in ds.data_vars and np.iscomplexobj(ds['C12'].values)          # input reassembled (nd/filters.py:188-189)
+    assert set(out.data_vars) == {'C11', 'C12__re', 'C12__im'}                   # result keeps the split parts (quirk)

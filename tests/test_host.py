@@ -1,0 +1,199 @@
+"""
+CPU tests of the host side (run with -m "not gpu"): the C-ABI library loads and exports every symbol
+include/ndnlm.h declares, plans are geometry-only and can be created without a GPU, the Python mirror
+keeps the reference interface (names, argument meaning, errors), and NOTHING computes on the CPU.
+"""
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nd_b200 import _lib, device
+from nd_b200.dataset import Dataset, generate_test_dataset
+from nd_b200.filters import Filter, NLMeansFilter, nlmeans
+from nd_b200._filters import _pixelwise_nlmeans_3d, find_weight
+from nd_b200.shard import ShardPlan
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI -------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ndnlm.h")).read()
+    declared = set(re.findall(r"\b(ndnlm_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS)
+    L = _lib.lib()
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert b"sm_100a" in L.ndnlm_version()
+
+
+def test_no_oracle_import_in_product():
+    """The product path must never route through the oracle (or any CPU fallback)."""
+    for root, _, files in os.walk(os.path.join(ROOT, "nd_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, fn)).read()
+                assert "import oracle" not in text and "from oracle" not in text, fn
+
+
+def test_plan_roles_and_tiles_cfg3():
+    p = device.Plan((4096, 4096, 32, 4), (5, 5, 2), (1, 1, 1), 0.25, 0.5)
+    d = p.describe()
+    assert p.is_tiled and "nlm_tiled" in d["kernel"]
+    assert d["role_axis_WRX"] == [0, 2, 1]            # W = y, R = time, X = x
+    assert d["pad_WRX"] == [6, 3, 6]
+    assert d["n_offsets"] == 604
+    assert d["smem_bytes"] <= 232448
+    assert d["box_WRX"][1] % 2 == 1                   # odd R pitch (bank-conflict-free LDS.128)
+    assert d["padded_bytes"] == (4096 + 12) * (4096 + 12) * (32 + 6) * 16
+
+
+@pytest.mark.parametrize("shape,r,f,n_eff,F", [
+    ((1, 206, 500, 4), (0, 3, 3), (0, 1, 1), -1, 1455),            # cfg1  
+    ((1024, 1024, 24, 4), (5, 5, 1), (1, 1, 1), -1, 11599),        # cfg2
+    ((4096, 4096, 32, 4), (5, 5, 2), (1, 1, 1), -1, 19343),        # cfg3
+    ((16384, 16384, 64, 4), (7, 7, 2), (2, 2, 2), -1, 35983),      # cfg4
+    ((32768, 32768, 128, 6), (10, 10, 3), (2, 2, 2), -1, 129633),  # cfg5
+    ((4096, 4096, 32, 4), (5, 5, 2), (1, 1, 1), 50, 19343 + 2 * 604),
+])
+def test_algorithmic_flops_match_baseline_table(shape, r, f, n_eff, F):
+    p = device.Plan(shape, r, f, 0.25, 0.5, n_eff)
+    assert p.flops_per_voxel == F
+    assert p.voxels == shape[0] * shape[1] * shape[2]
+
+
+def test_plan_kernel_selection():
+    assert device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64).kernel_name == "nlm_generic<double>"
+    assert "zero_dist" in device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, semantics="reference_compiled").kernel_name
+    assert device.Plan((40, 50, 30, 4), (2, 2, 1), (0, 0, 0), 1, 1, semantics="reference_compiled").is_tiled
+    assert device.Plan((1, 206, 500, 4), (0, 3, 3), (0, 1, 1), 1, 1).is_tiled
+    assert not device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, kernel="generic").is_tiled
+    with pytest.raises(ValueError):
+        device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64, kernel="tiled")
+
+
+def test_plan_errors_map_to_reference_exceptions():
+    with pytest.raises(TypeError):                                   # fused `floating` dispatch failure
+        device.Plan((4, 5, 6, 2), (1, 1, 1), (0, 0, 0), 1, 1, dtype=np.int32)
+    with pytest.raises(ValueError, match="reflection"):              # r+f > N-1 is UB in the reference
+        device.Plan((4, 5, 6, 2), (3, 1, 1), (1, 1, 1), 1, 1)
+    with pytest.raises(ValueError):
+        device.Plan((4, 5, 6), (1, 1, 1), (0, 0, 0), 1, 1)
+    with pytest.raises(ValueError):
+        device.Plan((4, 5, 6, 2), (1, 1, 1), (0, 0, 0), 1, 1, semantics="bogus")
+    with pytest.raises(ValueError):
+        device.Plan((4, 5, 6, 2), (1, 1, 1), (0, 0, 0), 1, 0.0)
+
+
+def test_halo_message_size():
+    p = device.Plan((64, 80, 16, 4), (3, 3, 1), (1, 1, 1), 1, 1)
+    assert p.halo_bytes(0) == 4 * (80 + 8) * (16 + 4) * 16           # (r+f) rows x padded X x padded T x float4
+    assert device.Plan((64, 80, 16, 4), (0, 3, 1), (0, 1, 1), 1, 1).halo_bytes(0) == 0
+
+
+# ---- the reference's Python interface ------------------------------------------------------------
+def test_filter_signature_is_the_reference_plugin_boundary():
+    # nd/tests/test_filters_common.py:37-41
+    assert list(inspect.signature(NLMeansFilter._filter).parameters) == ['self', 'arr', 'axes', 'output']
+    assert issubclass(NLMeansFilter, Filter)
+    assert NLMeansFilter.per_variable is False and NLMeansFilter.supports_complex is False
+    params = inspect.signature(NLMeansFilter.apply).parameters
+    assert list(params)[:3] == ['self', 'ds', 'inplace'] and 'njobs' in params
+    sig = inspect.signature(NLMeansFilter.__init__).parameters
+    assert [sig[k].default for k in ('dims', 'r', 'sigma', 'h', 'f', 'n_eff')] == [('y', 'x'), 1, 1, 1, 1, -1]
+    assert list(inspect.signature(_pixelwise_nlmeans_3d).parameters)[:7] == ['arr', 'output', 'r', 'f', 'sigma', 'h', 'n_eff']
+    assert 'dims' in inspect.signature(nlmeans).parameters and 'ds' in inspect.signature(nlmeans).parameters
+
+
+def test_constructor_matches_reference():
+    # nd/filters.py:414-422: scalar r is broadcast; f_i = f if r_i > 0 else 0; uint32 arrays
+    flt = NLMeansFilter(dims=('y', 'x', 'time'), r=(2, 3, 0), f=2)
+    assert flt.r.dtype == np.uint32 and flt.f.dtype == np.uint32
+    assert list(flt.r) == [2, 3, 0] and list(flt.f) == [2, 2, 0]
+    assert list(NLMeansFilter(dims=('y', 'x'), r=3).r) == [3, 3]
+    assert flt._buffer('y') == 4 and flt._buffer('x') == 5 and flt._buffer('time') == 0 and flt._buffer('band') == 0
+
+
+def test_parallel_dimension_rule():
+    ds = generate_test_dataset(dims={'y': 20, 'x': 30, 'time': 10})
+    assert NLMeansFilter(dims=('y', 'x'))._parallel_dimension(ds) == 'time'      # largest non-filter dim
+    assert NLMeansFilter(dims=('y', 'x', 'time'))._parallel_dimension(ds) == 'x'  # else largest dim
+
+
+def test_zero_radius_and_empty_dims_are_exact_identity():
+    # nd/tests/test_nlmeans_filter.py:17-25 -- exact, float64 in -> float64 out, no device needed
+    ds = generate_test_dataset(dims={'y': 20, 'x': 20, 'time': 10})
+    out = NLMeansFilter(dims=('y', 'x'), r=0, f=1, sigma=1, h=1).apply(ds)
+    assert isinstance(out, Dataset) and ds.equals(out) and out is not ds
+    assert out.attrs == ds.attrs and list(out.coords) == list(ds.coords)
+    assert ds.equals(NLMeansFilter(dims=(), r=1, f=1, sigma=1, h=1).apply(ds))
+    assert ds.equals(nlmeans(ds, dims=('y', 'x'), r=0))
+    with pytest.raises(NotImplementedError):
+        NLMeansFilter(dims=('y', 'x'), r=0).apply(ds, inplace=True)
+
+
+def test_compute_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    a = np.zeros((4, 5, 6, 2), np.float32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _pixelwise_nlmeans_3d(a, np.empty_like(a), np.array([1, 1, 1], np.uint32), np.array([0, 0, 0], np.uint32), 1.0, 1.0)
+    ds = generate_test_dataset(dims={'y': 8, 'x': 8, 'time': 3})
+    with pytest.raises(RuntimeError):
+        NLMeansFilter(dims=('y', 'x'), r=1).apply(ds)
+
+
+def test_entry_point_argument_errors():
+    a = np.zeros((4, 5, 6, 2), np.float32)
+    u = lambda *v: np.array(v, np.uint32)
+    with pytest.raises(TypeError):
+        _pixelwise_nlmeans_3d(a.astype(np.int32), np.empty_like(a, dtype=np.int32), u(1, 1, 1), u(0, 0, 0), 1.0, 1.0)
+    with pytest.raises(TypeError):
+        _pixelwise_nlmeans_3d(a, np.empty_like(a, dtype=np.float64), u(1, 1, 1), u(0, 0, 0), 1.0, 1.0)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        _pixelwise_nlmeans_3d(a, np.empty_like(a), np.array([1, 1, 1], np.int64), u(0, 0, 0), 1.0, 1.0)
+    with pytest.raises(ValueError):
+        _pixelwise_nlmeans_3d(a[0], np.empty_like(a[0]), u(1, 1, 1), u(0, 0, 0), 1.0, 1.0)
+
+
+def test_find_weight_closed_form():
+    # nd/_filters.pyx:297-314
+    S, Q, n = 26.0, 26.0, 5.0
+    w = find_weight(S, Q, n)
+    assert abs((S + w) ** 2 / (Q + w * w) - n) < 1e-12
+    with pytest.raises(ValueError, match="No solution"):
+        find_weight(1.0, 1.0, 20.0)
+
+
+# ---- shard plan == xr_split chunking (nd/utils.py:305-310) ---------------------------------------
+@pytest.mark.parametrize("n,chunks,halo", [(20, 2, 2), (21, 2, 3), (4096, 8, 6), (10, 3, 1), (7, 8, 0)])
+def test_shard_plan_matches_xr_split(n, chunks, halo):
+    sp = ShardPlan(n, chunks, halo)
+    chunksize = int(np.ceil(n / chunks))
+    expected = [(i * chunksize, min((i + 1) * chunksize, n)) for i in range(chunks) if i * chunksize < n]
+    assert sp.ranges == expected
+    assert sp.ranges[0][0] == 0 and sp.ranges[-1][1] == n
+    for i, (lo, hi) in enumerate(sp.ranges):
+        assert sp.buffered_range(i) == (max(lo - halo, 0), min(hi + halo, n))
+        assert sp.edges(i) == ('reflect' if i == 0 else 'halo', 'reflect' if i == sp.nshards - 1 else 'halo')
+
+
+def test_shard_plan_rejects_shards_smaller_than_halo():
+    with pytest.raises(ValueError):
+        ShardPlan(16, 8, 6)
+
+
+def test_dataset_standin_roundtrip():
+    ds = generate_test_dataset(dims={'y': 6, 'x': 7, 'time': 3})
+    assert list(ds.data_vars) == ['C11', 'C12__im', 'C12__re', 'C22']
+    assert ds['C11'].dims == ('y', 'x', 'time') and ds['C11'].values.dtype == np.float64
+    assert list(ds.dims) == ['time', 'x', 'y']                      # alphabetical like xarray
+    t0 = ds.isel(time=0)
+    assert t0['C11'].dims == ('y', 'x') and t0['C11'].shape == (6, 7)
+    c = ds.copy(deep=True)
+    c['C11'].values[0, 0, 0] += 1
+    assert not ds.equals(c)

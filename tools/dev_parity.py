@@ -74,6 +74,15 @@ def run_case(i):
 if __name__ == "__main__":
     if "--case" in sys.argv:
         run_case(int(sys.argv[sys.argv.index("--case") + 1]))
+    elif "--inproc" in sys.argv:      # all cases in this process (fast; a CUDA fault kills the sweep)
+        for i in range(len(CASES)):
+            env_keys = list(CASES[i][7])
+            try:
+                run_case(i)
+            except Exception as e:
+                print("FAILED case %d %s: %r" % (i, CASES[i][0], e), flush=True)
+            for k in env_keys:
+                os.environ.pop(k, None)
     else:
         for i in range(len(CASES)):
             p = subprocess.run([sys.executable, __file__, "--case", str(i)], capture_output=True, text=True, timeout=300)
