@@ -33,7 +33,7 @@ def _as_u32_3(x, name):
 
 
 def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=None, kernel='auto',
-                          njobs=1, shard_axis=None, devices=None):
+                          njobs=1, shard_axis=None, devices=None, pipeline=None, slab_rows=None):
     """
     GPU replacement of `nd._filters._pixelwise_nlmeans_3d` (reference nd/_filters.pyx:320-420).
 
@@ -44,6 +44,7 @@ def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=No
     semantics   : 'as_written' (default) or 'reference_compiled' (SURVEY.md D1); also ND_NLM_SEMANTICS.
     njobs       : number of GPUs to shard over along `shard_axis` (default: the largest axis that is
                   not filtered, else the largest axis -- reference nd/filters.py:424-435).
+    pipeline    : stream host arrays through the GPU in slabs with overlapped copies (default: arrays >= 256 MiB).
     devices     : optional explicit CUDA device index per shard (e.g. [0, 0] exercises the shard /
                   halo-exchange layer on a single GPU).
     """
@@ -76,6 +77,15 @@ def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=No
         njobs = len(devices)
     if njobs > 1 or devices is not None:
         _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis, devices)
+        return
+
+    # large host arrays: slab pipeline (H2D / kernels / D2H overlapped), nd_b200/stream.py
+    from . import stream as _stream
+    if pipeline is None:
+        pipeline = arr.nbytes >= (256 << 20)
+    if pipeline and _stream.can_pipeline(arr, output) and (r3[0] + f3[0]) * 8 <= arr.shape[0]:
+        _stream.apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff, semantics=semantics, kernel=kernel,
+                                     slab_rows=slab_rows)
         return
 
     plan = dev.Plan(arr.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)

@@ -1,0 +1,129 @@
+"""
+Host <-> device slab pipeline for arrays that live in HOST memory.
+
+`_pixelwise_nlmeans_3d(arr, output, ...)` on host arrays is PCIe-bound once the kernel runs at
+~1 Gvoxel/s (32 B per voxel each way).  This driver cuts the cube into slabs along axis 0 -- the same
+1-D split with an `r+f` buffer the reference uses for its worker pool (`xr_split` / `xr_merge`,
+nd/utils.py:288-340; also the `buffer` of nd/tiling.py:18-106) -- and overlaps, on three CUDA streams
+with double-buffered device slabs,
+
+    H2D of slab i+1   |   stage + nlm kernel + unstage of slab i   |   D2H of slab i-1.
+
+Every slab is filtered on its buffered range and only its interior rows are kept, exactly like
+`xr_merge` strips the buffers, so the result equals the unsliced call (the discarded rows are the only
+ones affected by the cut).
+"""
+import numpy as np
+import torch
+
+from . import device as dev
+from .shard import ShardPlan
+
+
+def dense_axis_order(a):
+    """Axes of `a` from slowest to fastest if `a` is a dense, non-overlapping (possibly transposed)
+    block of memory with positive strides; else None."""
+    if any(s <= 0 for s in a.strides) or a.size == 0:
+        return None
+    order = sorted(range(a.ndim), key=lambda k: (-a.strides[k], k))
+    expect = a.itemsize
+    for k in reversed(order):
+        if a.shape[k] != 1 and a.strides[k] != expect:
+            return None
+        expect *= a.shape[k]
+    return order
+
+
+def can_pipeline(arr, output, min_rows=64):
+    return (arr.ndim == 4 and arr.shape == output.shape and arr.shape[0] >= 2 * min_rows
+            and dense_axis_order(arr) is not None and dense_axis_order(arr) == dense_axis_order(output))
+
+
+def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None, kernel='auto', slab_rows=None):
+    """Filter host array `arr` into host array `output` through the slab pipeline.  Raises
+    ValueError('No solution') like the reference when find_weight fails anywhere."""
+    order = dense_axis_order(arr)
+    if order is None or order != dense_axis_order(output):
+        raise ValueError('apply_host_pipelined needs dense arrays with identical memory layout')
+    n0 = arr.shape[0]
+    halo = int(r3[0]) + int(f3[0])
+    if slab_rows is None:
+        row_bytes = arr.itemsize * int(np.prod(arr.shape[1:]))
+        slab_rows = max(4 * halo + 16, min(n0, (1 << 30) // max(row_bytes, 1)))      # ~1 GiB per slab
+    nslab = max(1, -(-n0 // slab_rows))
+    sp = ShardPlan(n0, nslab, halo)
+    device = torch.device('cuda', torch.cuda.current_device())
+    tdtype = torch.float32 if arr.dtype == np.float32 else torch.float64
+
+    # host views in memory order: hv[outer..., rows, inner...] with every [outer][lo:hi] block contiguous
+    k0 = order.index(0)
+    hv_in = torch.from_numpy(arr.transpose(order))
+    hv_out = torch.from_numpy(output.transpose(order))
+    inv = [order.index(a) for a in range(4)]
+    max_rows = max(sp.buffered_range(i)[1] - sp.buffered_range(i)[0] for i in range(sp.nshards))
+    mem_shape = [arr.shape[a] for a in order]
+    mem_shape[k0] = max_rows
+    d_in = [torch.empty(mem_shape, dtype=tdtype, device=device) for _ in range(2)]
+    d_out = [torch.empty(mem_shape, dtype=tdtype, device=device) for _ in range(2)]
+
+    plans = {}
+    pad_bytes = out_bytes = 0
+    for i in range(sp.nshards):
+        blo, bhi = sp.buffered_range(i)
+        shape = (bhi - blo,) + tuple(arr.shape[1:])
+        if shape not in plans:
+            plans[shape] = dev.Plan(shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)
+            pad_bytes = max(pad_bytes, plans[shape].padded_bytes)
+            out_bytes = max(out_bytes, plans[shape].out_bytes)
+    padded = [torch.empty(pad_bytes, dtype=torch.uint8, device=device) for _ in range(2)]
+    internal = [torch.empty(out_bytes, dtype=torch.uint8, device=device) for _ in range(2)]
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+
+    cur = torch.cuda.current_stream()
+    s_h2d, s_comp, s_d2h = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    for s in (s_h2d, s_comp, s_d2h):
+        s.wait_stream(cur)
+    ev_in_free = [None, None]     # compute on buffer b finished -> d_in[b] may be overwritten
+    ev_out_free = [None, None]    # D2H from buffer b finished   -> d_out[b] may be overwritten
+
+    def block(t, lo, hi):
+        idx = [slice(None)] * 4
+        idx[k0] = slice(lo, hi)
+        return t[tuple(idx)]
+
+    for i in range(sp.nshards):
+        b = i & 1
+        lo, hi = sp.ranges[i]
+        blo, bhi = sp.buffered_range(i)
+        rows = bhi - blo
+        with torch.cuda.stream(s_h2d):
+            if ev_in_free[b] is not None:
+                s_h2d.wait_event(ev_in_free[b])
+            block(d_in[b], 0, rows).copy_(block(hv_in, blo, bhi), non_blocking=True)
+            ev_h2d = torch.cuda.Event()
+            ev_h2d.record(s_h2d)
+        with torch.cuda.stream(s_comp):
+            s_comp.wait_event(ev_h2d)
+            if ev_out_free[b] is not None:
+                s_comp.wait_event(ev_out_free[b])
+            plan = plans[(rows,) + tuple(arr.shape[1:])]
+            a_in = block(d_in[b], 0, rows).permute(inv)          # logical (N0, N1, N2, V) view
+            a_out = block(d_out[b], 0, rows).permute(inv)
+            plan.stage(a_in, padded[b])
+            plan.run(padded[b], internal[b], flag)
+            plan.unstage(internal[b], a_out)
+            ev_comp = torch.cuda.Event()
+            ev_comp.record(s_comp)
+            ev_in_free[b] = ev_comp
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(ev_comp)
+            block(hv_out, lo, hi).copy_(block(d_out[b], lo - blo, hi - blo), non_blocking=True)
+            ev_d2h = torch.cuda.Event()
+            ev_d2h.record(s_d2h)
+            ev_out_free[b] = ev_d2h
+    for s in (s_h2d, s_comp, s_d2h):
+        cur.wait_stream(s)
+    cur.synchronize()
+    if int(flag.item()):
+        raise ValueError('No solution')
+    return sp.nshards

@@ -266,3 +266,40 @@ def test_complex_variables_are_split_and_reassembled(dev):
     out = NLMeansFilter(dims=('y', 'x'), r=1, sigma=1, h=1).apply(ds)
     assert 'C12' in ds.data_vars and np.iscomplexobj(ds['C12'].values)          # input reassembled (nd/filters.py:188-189)
     assert set(out.data_vars) == {'C11', 'C12__re', 'C12__im'}                   # result keeps the split parts (quirk)
+
+
+# ---- host slab pipeline ---------------------------------------------------------
+@pytest.mark.parametrize("vmajor", [False, True])
+def test_host_slab_pipeline_equals_monolithic_bitwise(dev, vmajor):
+    """H2D / kernels / D2H overlapped over y-slabs with an r+f buffer == one monolithic call, bit for bit,
+    for C-contiguous arrays and for the variable-major views Filter.apply produces."""
+    from nd_b200._filters import _pixelwise_nlmeans_3d
+    a = sar_like((150, 48, 8, 4), seed=12, dtype=np.float32)
+    if vmajor:
+        a = np.moveaxis(np.ascontiguousarray(np.moveaxis(a, -1, 0)), 0, -1)
+    r, f = np.array([3, 3, 1], np.uint32), np.array([1, 1, 1], np.uint32)
+    mono = np.empty_like(a)
+    _pixelwise_nlmeans_3d(a, mono, r, f, 0.3, 0.6, pipeline=False)
+    piped = np.full_like(a, np.nan)
+    _pixelwise_nlmeans_3d(a, piped, r, f, 0.3, 0.6, pipeline=True, slab_rows=40)
+    assert np.array_equal(mono, piped)
+    piped2 = np.full_like(a, np.nan)
+    _pixelwise_nlmeans_3d(a, piped2, r, f, 0.3, 0.6, pipeline=True, slab_rows=64)
+    assert np.array_equal(mono, piped2)
+
+
+def test_host_slab_pipeline_pinned_and_neff_error(dev):
+    import torch
+    from nd_b200._filters import _pixelwise_nlmeans_3d
+    h_in = torch.empty((160, 40, 6, 4), dtype=torch.float32, pin_memory=True)
+    h_in.copy_(torch.from_numpy(sar_like((160, 40, 6, 4), seed=13, dtype=np.float32)))
+    h_out = torch.empty_like(h_in, pin_memory=True)
+    a, o = h_in.numpy(), h_out.numpy()
+    r, f = np.array([2, 2, 1], np.uint32), np.array([1, 1, 1], np.uint32)
+    _pixelwise_nlmeans_3d(a, o, r, f, 0.3, 0.6, pipeline=True, slab_rows=48)
+    mono = np.empty_like(a)
+    _pixelwise_nlmeans_3d(a, mono, r, f, 0.3, 0.6, pipeline=False)
+    assert np.array_equal(o, mono)
+    with pytest.raises(ValueError, match="No solution"):
+        _pixelwise_nlmeans_3d(a, o, np.array([1, 1, 1], np.uint32), np.array([0, 0, 0], np.uint32), 0.01, 0.01, 20.0,
+                              pipeline=True, slab_rows=48)
