@@ -180,27 +180,31 @@ extern "C" int ndnlm_plan_create(ndnlm_plan_t** out_plan, const int64_t shape[4]
     for (int a = 0; a < 3; ++a) { pl->r[a] = r[a]; pl->f[a] = f[a]; }
     pl->sigma = sigma; pl->h = h; pl->n_eff = n_eff; pl->semantics = semantics; pl->dtype = dtype;
 
-    // ---- role assignment: X = widest active axis, R = remaining active axis with the smallest search
-    //      radius, W = the rest (ties go to the later, i.e. faster-varying, axis) ----
+    // ---- role assignment.  It must NOT depend on the extent of axis 0, so that slabs / shards cut along
+    //      axis 0 (the usual 'y') run exactly the same arithmetic as the whole cube:
+    //        3 filtered axes: W = axis 0, X = the wider of axes 1 and 2 (tie: 2), R = the other;
+    //        2 filtered axes: the unfiltered axis is W; X = the later filtered axis unless only axis 0 is left, R = the other;
+    //        1 filtered axis: X = it; R, W = the rest (R the later one);   none: X = 2, R = 1, W = 0.
     bool active[3];
     int nact = 0;
     for (int a = 0; a < 3; ++a) { active[a] = (r[a] > 0 || f[a] > 0); nact += active[a]; }
-    int ax = -1, ar = -1, aw = -1;
-    auto pick = [&](bool want_active, bool any, auto better) {
-        int best = -1;
-        for (int a = 0; a < 3; ++a) {
-            if (a == ax || a == ar) continue;
-            if (!any && active[a] != want_active) continue;
-            if (best < 0 || better(a, best)) best = a;
-        }
-        return best;
-    };
-    auto larger_n = [&](int a, int b) { return shape[a] >= shape[b]; };
-    auto smaller_r = [&](int a, int b) { return r[a] < r[b] || (r[a] == r[b] && shape[a] <= shape[b]); };
-    ax = pick(true, nact == 0, larger_n);
-    if (nact >= 2) ar = pick(true, false, smaller_r);
-    else ar = pick(false, true, larger_n);
-    aw = pick(false, true, larger_n);
+    int ax = 2, ar = 1, aw = 0;
+    if (nact == 3) {
+        aw = 0;
+        ax = (shape[1] > shape[2]) ? 1 : 2;
+        ar = 3 - ax;
+    } else if (nact == 2) {
+        for (int a = 0; a < 3; ++a) if (!active[a]) aw = a;
+        int first = -1, second = -1;
+        for (int a = 0; a < 3; ++a) if (active[a]) { if (first < 0) first = a; else second = a; }
+        if (first == 0) { ax = second; ar = 0; }                       // axis 0 goes to the register role
+        else { ax = (shape[first] > shape[second]) ? first : second; ar = first + second - ax; }
+    } else if (nact == 1) {
+        for (int a = 0; a < 3; ++a) if (active[a]) ax = a;
+        ar = -1;
+        for (int a = 2; a >= 0; --a) if (a != ax && ar < 0) ar = a;
+        aw = 3 - ax - ar;
+    }
     pl->perm[ROLE_W] = aw; pl->perm[ROLE_R] = ar; pl->perm[ROLE_X] = ax;
 
     DevParams& P = pl->P;

@@ -303,3 +303,20 @@ def test_host_slab_pipeline_pinned_and_neff_error(dev):
     with pytest.raises(ValueError, match="No solution"):
         _pixelwise_nlmeans_3d(a, o, np.array([1, 1, 1], np.uint32), np.array([0, 0, 0], np.uint32), 0.01, 0.01, 20.0,
                               pipeline=True, slab_rows=48)
+
+
+# ---- real multi-GPU (skipped on a 1-GPU box) ----------------------------------------------------------
+def test_njobs_two_gpus_equals_one_gpu(dev):
+    """The reference's test_parallelized_filter (nd/tests/test_filters_common.py:54-60) with njobs = GPUs:
+    y-shards on two devices, halo rows over peer copies, == single-GPU result bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from nd_b200.dataset import generate_test_dataset
+    from nd_b200.filters import NLMeansFilter
+    ds = generate_test_dataset(dims={'y': 40, 'x': 30, 'time': 10}, dtype=np.float32)
+    for dims in (('x', 'y'), ('x', 'y', 'time')):
+        one = NLMeansFilter(dims=dims, r=2, sigma=1, h=1).apply(ds)
+        two = NLMeansFilter(dims=dims, r=2, sigma=1, h=1).apply(ds, njobs=2)
+        for v in ds.data_vars:
+            assert np.array_equal(one[v].values, two[v].values), (dims, v)
