@@ -13,7 +13,9 @@
  *                                                         (reference nd/filters.py:462-463).
  *
  * Everything here is plain C: pointers, sizes, no torch / C++ types.  All array pointers
- * are DEVICE pointers on the current CUDA device unless a parameter says "host".
+ * are DEVICE pointers unless a parameter says "host"; the library binds the device that owns the
+ * buffers itself (it carries its own CUDA runtime, independent of the caller's "current device"),
+ * and `stream` must be a stream of that device.
  * The caller owns every buffer; the library allocates nothing that outlives a call except
  * the plan object.  Functions return 0 on success or a negative NDNLM_E* code and never
  * throw; `ndnlm_last_error()` gives the message for the calling thread.
@@ -153,7 +155,7 @@ int ndnlm_synth_cube(float* out, int64_t ny_local, int64_t nx, int64_t nt, int32
  * FP32 FMA-chain microbenchmark on the current device (runs for about `seconds`): the measured
  * CUDA-core peak in TFLOP/s, reported by bench.py beside the nominal SMs*128*2*clock roofline.
  */
-int ndnlm_measure_fp32_peak(double* tflops, double seconds, void* stream);
+int ndnlm_measure_fp32_peak(double* tflops, double seconds, int device, void* stream);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t ndnlm_launch_count(void);

@@ -92,7 +92,7 @@ def lib():
     L.ndnlm_synth_cube.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                    ctypes.c_int64, ctypes.c_uint64, vp]
     L.ndnlm_synth_cube.restype = ctypes.c_int
-    L.ndnlm_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_double, vp]
+    L.ndnlm_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.c_int, vp]
     L.ndnlm_measure_fp32_peak.restype = ctypes.c_int
     L.ndnlm_launch_count.argtypes = []
     L.ndnlm_launch_count.restype = ctypes.c_int64

@@ -39,6 +39,32 @@ static int fail(int code, const char* fmt, ...) {
             return fail(NDNLM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// This library links its own (static) CUDA runtime, whose "current device" is separate from the caller's
+// runtime (PyTorch ships another libcudart).  Every launching entry point therefore binds the device that
+// OWNS the buffers it was given and restores the previous one on exit; launching on the wrong device would
+// make TMA read peer memory and never complete.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(const void* ptr) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            ok = false;
+            return;
+        }
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        if (prev != attr.device && cudaSetDevice(attr.device) != cudaSuccess) ok = false;
+        if (prev == attr.device) prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define GUARD_DEVICE(ptr)                                                                    \
+    DeviceGuard guard_(ptr);                                                                 \
+    if (!guard_.ok) return fail(NDNLM_EINVAL, "%s is not a CUDA device pointer", #ptr)
+
 static inline unsigned blocks_for(long long total, int threads) { return unsigned((total + threads - 1) / threads); }
 
 // ------------------------------------------------------------------------------------------
@@ -51,12 +77,16 @@ template <int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
 static cudaError_t launch_tiled(const CUtensorMap& tmap, const DevParams& P, const float4* padded, float4* out,
                                 int* err, int grid, size_t smem, cudaStream_t st) {
     auto kern = nlm_tiled_kernel<NV4, FW, FX, FR, L, NWARPS, CH, NEFF>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
+    // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
+    static std::atomic<bool> opted_in[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !opted_in[dev].load()) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) opted_in[dev].store(true);
+    }
     kern<<<grid, NWARPS * 32, smem, st>>>(tmap, P, padded, out, err);
     return cudaGetLastError();
 }
@@ -338,6 +368,7 @@ static int role_of_axis(const ndnlm_plan* pl, int axis) {
 extern "C" int ndnlm_stage(const ndnlm_plan_t* pl, const void* arr, const int64_t arr_strides[4], void* padded,
                            int shard_axis, int lo_edge, int hi_edge, void* stream) {
     if (!pl || !arr || !arr_strides || !padded) return fail(NDNLM_EINVAL, "null argument");
+    GUARD_DEVICE(padded);
     cudaStream_t st = (cudaStream_t)stream;
     StageParams S;
     fill_stage_params(pl, arr_strides, S);
@@ -366,6 +397,7 @@ extern "C" int ndnlm_stage(const ndnlm_plan_t* pl, const void* arr, const int64_
 extern "C" int ndnlm_unstage(const ndnlm_plan_t* pl, const void* internal, void* output, const int64_t out_strides[4],
                              void* stream) {
     if (!pl || !internal || !output || !out_strides) return fail(NDNLM_EINVAL, "null argument");
+    GUARD_DEVICE(internal);
     cudaStream_t st = (cudaStream_t)stream;
     StageParams S;
     fill_stage_params(pl, out_strides, S);
@@ -419,6 +451,7 @@ template <bool PACK>
 static int halo_copy(const ndnlm_plan* pl, void* padded, int axis, int side, void* msg, cudaStream_t st) {
     if (!pl || !padded || !msg) return fail(NDNLM_EINVAL, "null argument");
     if (axis < 0 || axis > 2 || side < 0 || side > 1) return fail(NDNLM_EINVAL, "bad axis/side");
+    GUARD_DEVICE(padded);
     const int role = role_of_axis(pl, axis);
     const DevParams& P = pl->P;
     const long long rows = P.pad[role];
@@ -471,6 +504,7 @@ static encode_tiled_fn get_encode_fn() {
 
 extern "C" int ndnlm_run(const ndnlm_plan_t* pl, const void* padded, void* out_internal, int32_t* err_flag, void* stream) {
     if (!pl || !padded || !out_internal || !err_flag) return fail(NDNLM_EINVAL, "null argument");
+    GUARD_DEVICE(padded);
     cudaStream_t st = (cudaStream_t)stream;
     const DevParams& P = pl->P;
     if (pl->kernel == NDNLM_KERNEL_TILED) {
@@ -519,6 +553,7 @@ extern "C" size_t ndnlm_workspace_bytes(const ndnlm_plan_t* pl) {
 extern "C" int ndnlm_apply(const ndnlm_plan_t* pl, const void* arr, const int64_t arr_strides[4], void* output,
                            const int64_t out_strides[4], void* workspace, void* stream) {
     if (!pl || !workspace) return fail(NDNLM_EINVAL, "null argument");
+    GUARD_DEVICE(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* ws = (unsigned char*)workspace;
     void* padded = ws;
@@ -544,6 +579,7 @@ extern "C" int ndnlm_apply(const ndnlm_plan_t* pl, const void* arr, const int64_
 extern "C" int ndnlm_synth_cube(float* out, int64_t ny_local, int64_t nx, int64_t nt, int32_t V, int64_t y_offset,
                                 uint64_t seed, void* stream) {
     if (!out || ny_local < 1 || nx < 1 || nt < 1 || V < 1) return fail(NDNLM_EINVAL, "bad argument");
+    GUARD_DEVICE(out);
     const long long total = (long long)ny_local * nx * nt;
     synth_cube_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(out, ny_local, nx, nt, V, y_offset, seed);
     g_launches++;
@@ -567,11 +603,12 @@ __global__ void __launch_bounds__(1024) fp32_peak_kernel(float* out, float a, fl
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-extern "C" int ndnlm_measure_fp32_peak(double* tflops, double seconds, void* stream) {
+extern "C" int ndnlm_measure_fp32_peak(double* tflops, double seconds, int device, void* stream) {
     if (!tflops) return fail(NDNLM_EINVAL, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    int dev = 0, sms = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
+    int dev = device, sms = 0, prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(dev));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     float* out = nullptr;
     CUDA_TRY(cudaMalloc(&out, sizeof(float) * size_t(sms) * 2 * 1024));
@@ -595,6 +632,7 @@ extern "C" int ndnlm_measure_fp32_peak(double* tflops, double seconds, void* str
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(out);
+    cudaSetDevice(prev);
     *tflops = best * 1e-12;
     return NDNLM_OK;
 }

@@ -23,6 +23,9 @@
 
 #include "nlm_common.cuh"
 
+#ifndef NDNLM_KEEP_OWN
+#define NDNLM_KEEP_OWN 0   // 1: keep my own exchanged sums in registers instead of re-reading them from shared memory
+#endif
 #ifndef NDNLM_FOLD_T
 #define NDNLM_FOLD_T double   // type of the second-level weight-sum accumulators
 #endif
@@ -113,6 +116,19 @@ __device__ __forceinline__ void column_box_sum(const float (&s)[L + 2 * F], floa
     }
 }
 
+// F == 1 variant that shares the middle pair between two neighbouring outputs: 3 adds per 2 outputs
+// instead of 4.  The association depends on the parity of the output index inside the column, so it is
+// only used where the R axis is never cut by slabs / shards (three filtered axes: W is axis 0).
+template <int L>
+__device__ __forceinline__ void column_box_sum_paired(const float (&s)[L + 2], float (&o)[L]) {
+#pragma unroll
+    for (int k = 0; k < L / 2; ++k) {
+        const float m = s[2 * k + 1] + s[2 * k + 2];
+        o[2 * k] = s[2 * k] + m;
+        o[2 * k + 1] = m + s[2 * k + 3];
+    }
+}
+
 // Direct (2F+1)-term sum across lanes, fixed order (lane x gets x-F..x+F).
 template <int F>
 __device__ __forceinline__ float lane_box_sum(float v) {
@@ -144,6 +160,27 @@ __device__ __forceinline__ void dispatch_chunk(const int nj, const bool centre, 
         } else {
             dispatch_chunk<MAXJ - 1>(nj, centre, fn);
         }
+    }
+}
+
+// The same for two values at once (a register pair): the adds are packed FADD2.
+template <int F>
+__device__ __forceinline__ float2 lane_box_sum2(const float2 v) {
+    if constexpr (F == 0) {
+        return v;
+    } else if constexpr (F == 1) {
+        const float2 a = make_float2(__shfl_up_sync(FULL_MASK, v.x, 1), __shfl_up_sync(FULL_MASK, v.y, 1));
+        const float2 b = make_float2(__shfl_down_sync(FULL_MASK, v.x, 1), __shfl_down_sync(FULL_MASK, v.y, 1));
+        return __fadd2_rn(__fadd2_rn(a, v), b);
+    } else {
+        float2 t = v;
+#pragma unroll
+        for (int d = 1; d <= F; ++d) {
+            const float2 a = make_float2(__shfl_up_sync(FULL_MASK, v.x, d), __shfl_up_sync(FULL_MASK, v.y, d));
+            const float2 b = make_float2(__shfl_down_sync(FULL_MASK, v.x, d), __shfl_down_sync(FULL_MASK, v.y, d));
+            t = __fadd2_rn(t, __fadd2_rn(a, b));
+        }
+        return t;
     }
 }
 
@@ -248,7 +285,8 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     }
 
     float2 acc_lo[NV4][L], acc_hi[NV4][L];
-    float S[L], M[L], Q[L];
+    float2 S2[L / 2], Q2[L / 2];
+    float M[L];
     NDNLM_FOLD_T Sd[L], Qd[L];
 #pragma unroll
     for (int o = 0; o < L; ++o) {
@@ -257,13 +295,16 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
             acc_lo[q][o] = make_float2(0.f, 0.f);
             acc_hi[q][o] = make_float2(0.f, 0.f);
         }
-        S[o] = 0.f;
         M[o] = 0.f;
-        Q[o] = 0.f;
         Sd[o] = 0;
         Qd[o] = 0;
     }
 
+#pragma unroll
+    for (int o2 = 0; o2 < L / 2; ++o2) {
+        S2[o2] = make_float2(0.f, 0.f);
+        Q2[o2] = make_float2(0.f, 0.f);
+    }
     const int rW = P.rad[0], rR = P.rad[1], rX = P.rad[2];
     const float2 c1 = make_float2(P.c1, P.c1);
     const float2 nc2 = make_float2(-P.c2, -P.c2);
@@ -271,13 +312,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     constexpr int EX_J = NWARPS * (L / 2) * 32;                     // float2 stride between R-offsets j
     constexpr int EX_ROW = (L / 2) * 32;                            // float2 stride between W rows (FW>0: 1 warp/row)
     uint32_t xpar = 0;                                              // parity of the current exchange round
-    bool first_publish = true;
-    int nreaders = 0;
-    if constexpr (FW > 0) {
-#pragma unroll
-        for (int d = -FW; d <= FW; ++d)
-            if (d != 0 && wid + d >= FW && wid + d < NWARPS - FW) ++nreaders;
-    }
+    static_assert(FW == 0 || NWARPS >= 2 * FW + 2, "every row needs at least one reader");
 
     // One chunk of NJ consecutive R-offsets [ch0, ch0+NJ).  NJ is a compile-time constant so the body is
     // straight-line code the scheduler can interleave freely.  CENTRE: the chunk contains the centre
@@ -286,7 +321,8 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         constexpr int NJ = decltype(nj_tag)::value;
         constexpr bool CENTRE = decltype(centre_tag)::value;
         constexpr int WNJ = E + NJ - 1;
-        bool waited = false;
+        if constexpr (CENTRE && FW > 0) mbar_wait(mbar_empty + wid, xpar ^ 1);
+        float2 own[NDNLM_KEEP_OWN != 0 ? NJ : 1][L / 2];
 
         float4 n[NV4][WNJ];
 #pragma unroll
@@ -302,14 +338,11 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 const float w0_ = ex2_approx(-fmax_nan(t.x, 0.f));
                 const float w1_ = ex2_approx(-fmax_nan(t.y, 0.f));
                 const int o = 2 * o2;
-                S[o] += w0_;
-                S[o + 1] += w1_;
+                const float2 w2 = make_float2(w0_, w1_);
+                S2[o2] = __fadd2_rn(S2[o2], w2);
                 M[o] = fmaxf(M[o], w0_);
                 M[o + 1] = fmaxf(M[o + 1], w1_);
-                if constexpr (NEFF) {
-                    Q[o] = fmaf(w0_, w0_, Q[o]);
-                    Q[o + 1] = fmaf(w1_, w1_, Q[o + 1]);
-                }
+                if constexpr (NEFF) Q2[o2] = __ffma2_rn(w2, w2, Q2[o2]);
                 const float2 w0b = make_float2(w0_, w0_), w1b = make_float2(w1_, w1_);
 #pragma unroll
                 for (int q = 0; q < NV4; ++q) {
@@ -342,24 +375,24 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 s[e] = sq.x + sq.y;
             }
             float pr[L];
-            column_box_sum<FR, L>(s, pr);
+            if constexpr (FR == 1 && FW > 0) column_box_sum_paired<L>(s, pr);
+            else column_box_sum<FR, L>(s, pr);
             float2 px[L / 2];
 #pragma unroll
-            for (int o2 = 0; o2 < L / 2; ++o2) {
-                px[o2].x = lane_box_sum<FX>(pr[2 * o2]);
-                px[o2].y = lane_box_sum<FX>(pr[2 * o2 + 1]);
-            }
+            for (int o2 = 0; o2 < L / 2; ++o2) px[o2] = lane_box_sum2<FX>(make_float2(pr[2 * o2], pr[2 * o2 + 1]));
             if constexpr (FW == 0) {
                 weigh(px, j);
             } else {
                 // before the first store of this chunk: my readers must be done with the previous round
-                if (!waited) {
-                    if (!first_publish && nreaders > 0) mbar_wait(mbar_empty + wid, xpar ^ 1);
-                    first_publish = false;
-                    waited = true;
+                // (on a fresh barrier the wait for the "previous" parity returns at once)
+                if constexpr (!CENTRE) {
+                    if (j == 0) mbar_wait(mbar_empty + wid, xpar ^ 1);
                 }
 #pragma unroll
-                for (int o2 = 0; o2 < L / 2; ++o2) ex_own[j * EX_J + o2 * 32] = px[o2];
+                for (int o2 = 0; o2 < L / 2; ++o2) {
+                    ex_own[j * EX_J + o2 * 32] = px[o2];
+                    if constexpr (NDNLM_KEEP_OWN != 0) own[j][o2] = px[o2];
+                }
             }
         }
 
@@ -381,7 +414,10 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                     for (int o2 = 0; o2 < L / 2; ++o2) {
                         float2 t = ex_own[j * EX_J + o2 * 32 - FW * EX_ROW];
 #pragma unroll
-                        for (int d = -FW + 1; d <= FW; ++d) t = __fadd2_rn(t, ex_own[j * EX_J + o2 * 32 + d * EX_ROW]);
+                        for (int d = -FW + 1; d <= FW; ++d) {
+                            if (NDNLM_KEEP_OWN != 0 && d == 0) t = __fadd2_rn(t, own[j][o2]);
+                            else t = __fadd2_rn(t, ex_own[j * EX_J + o2 * 32 + d * EX_ROW]);
+                        }
                         D[o2] = t;
                     }
                     weigh(D, j);
@@ -411,12 +447,14 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         }
         // fold the fp32 partial weight sums of this W-offset row into float64
 #pragma unroll
-        for (int o = 0; o < L; ++o) {
-            Sd[o] += NDNLM_FOLD_T(S[o]);
-            S[o] = 0.f;
+        for (int o2 = 0; o2 < L / 2; ++o2) {
+            Sd[2 * o2] += NDNLM_FOLD_T(S2[o2].x);
+            Sd[2 * o2 + 1] += NDNLM_FOLD_T(S2[o2].y);
+            S2[o2] = make_float2(0.f, 0.f);
             if constexpr (NEFF) {
-                Qd[o] += NDNLM_FOLD_T(Q[o]);
-                Q[o] = 0.f;
+                Qd[2 * o2] += NDNLM_FOLD_T(Q2[o2].x);
+                Qd[2 * o2 + 1] += NDNLM_FOLD_T(Q2[o2].y);
+                Q2[o2] = make_float2(0.f, 0.f);
             }
         }
     }

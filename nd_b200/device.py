@@ -83,8 +83,10 @@ class Plan:
 
     # ---- the four steps ------------------------------------------------------------------
     @staticmethod
-    def _stream():
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(t=None):
+        """Current torch stream of the device that owns tensor `t` (or of the current device)."""
+        dev = t.device if t is not None else None
+        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
     def _check_arr(self, t):
         if not t.is_cuda:
@@ -99,27 +101,27 @@ class Plan:
         edge = {"reflect": _lib.EDGE_REFLECT, "halo": _lib.EDGE_HALO}
         _lib.check(self._L.ndnlm_stage(self._h, ctypes.c_void_p(arr.data_ptr()), _lib.i64(arr.stride()),
                                        ctypes.c_void_p(padded.data_ptr()), int(shard_axis), edge[lo_edge], edge[hi_edge],
-                                       self._stream()))
+                                       self._stream(padded)))
 
     def halo_bytes(self, axis):
         return int(self._L.ndnlm_halo_bytes(self._h, int(axis)))
 
     def halo_pack(self, padded, axis, side, msg):
         _lib.check(self._L.ndnlm_halo_pack(self._h, ctypes.c_void_p(padded.data_ptr()), int(axis), int(side),
-                                           ctypes.c_void_p(msg.data_ptr()), self._stream()))
+                                           ctypes.c_void_p(msg.data_ptr()), self._stream(padded)))
 
     def halo_unpack(self, padded, axis, side, msg):
         _lib.check(self._L.ndnlm_halo_unpack(self._h, ctypes.c_void_p(padded.data_ptr()), int(axis), int(side),
-                                             ctypes.c_void_p(msg.data_ptr()), self._stream()))
+                                             ctypes.c_void_p(msg.data_ptr()), self._stream(padded)))
 
     def run(self, padded, internal_out, err_flag):
         _lib.check(self._L.ndnlm_run(self._h, ctypes.c_void_p(padded.data_ptr()), ctypes.c_void_p(internal_out.data_ptr()),
-                                     ctypes.c_void_p(err_flag.data_ptr()), self._stream()))
+                                     ctypes.c_void_p(err_flag.data_ptr()), self._stream(padded)))
 
     def unstage(self, internal_out, output):
         self._check_arr(output)
         _lib.check(self._L.ndnlm_unstage(self._h, ctypes.c_void_p(internal_out.data_ptr()),
-                                         ctypes.c_void_p(output.data_ptr()), _lib.i64(output.stride()), self._stream()))
+                                         ctypes.c_void_p(output.data_ptr()), _lib.i64(output.stride()), self._stream(internal_out)))
 
     def apply(self, arr, output=None, workspace=None):
         """ndnlm_apply: stage + run + unstage on the current stream; raises ValueError('No solution')."""
@@ -131,7 +133,7 @@ class Plan:
             workspace = torch.empty(int(self._L.ndnlm_workspace_bytes(self._h)), dtype=torch.uint8, device=arr.device)
         _lib.check(self._L.ndnlm_apply(self._h, ctypes.c_void_p(arr.data_ptr()), _lib.i64(arr.stride()),
                                        ctypes.c_void_p(output.data_ptr()), _lib.i64(output.stride()),
-                                       ctypes.c_void_p(workspace.data_ptr()), self._stream()))
+                                       ctypes.c_void_p(workspace.data_ptr()), self._stream(arr)))
         return output
 
 
@@ -147,7 +149,7 @@ def synth_cube(ny_local, nx, nt, V=4, y_offset=0, seed=42, device="cuda"):
 def measure_fp32_peak(seconds=0.5):
     """Measured FP32 FMA peak of the current device in TFLOP/s (ndnlm_measure_fp32_peak)."""
     v = ctypes.c_double(0.0)
-    _lib.check(_lib.lib().ndnlm_measure_fp32_peak(ctypes.byref(v), float(seconds),
+    _lib.check(_lib.lib().ndnlm_measure_fp32_peak(ctypes.byref(v), float(seconds), int(torch.cuda.current_device()),
                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return float(v.value)
 
