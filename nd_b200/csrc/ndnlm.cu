@@ -164,21 +164,32 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti) {
     P.g[0] = gw; P.g[1] = gr; P.g[2] = gx;
     P.t[0] = gw - 2 * ti.fw; P.t[1] = gr * ti.L; P.t[2] = gx * txw;
     if (P.t[0] < 1) return false;
-    P.b[0] = gw + 2 * P.rad[0];
-    P.b[1] = gr * ti.L + 2 * ti.fr + 2 * P.rad[1];
-    P.b[1] |= 1;   // odd R pitch in shared memory: conflict-free LDS.128 across lanes (R is the fastest axis)
-    P.b[2] = gx * txw + 2 * ti.fx + 2 * P.rad[2];
-    for (int k = 0; k < 3; ++k)
-        if (P.b[k] > 256) return false;
+    // W search range in passes: the fewest passes whose box fits shared memory
+    const int ntw = 2 * P.rad[0] + 1;
+    bool fits = false;
+    size_t smem = 0;
+    for (int npass = 1; npass <= 4 && npass <= ntw && !fits; ++npass) {
+        const int per = (ntw + npass - 1) / npass;
+        P.npass = (ntw + per - 1) / per;
+        P.ntw_pass = per;
+        P.b[0] = gw + per - 1;
+        P.b[1] = gr * ti.L + 2 * ti.fr + 2 * P.rad[1];
+        P.b[1] |= 1;   // odd R pitch in shared memory: conflict-free LDS.128 across lanes (R is the fastest axis)
+        P.b[2] = gx * txw + 2 * ti.fx + 2 * P.rad[2];
+        bool ok = true;
+        for (int k = 0; k < 3; ++k)
+            if (P.b[k] > 256) ok = false;
+        const size_t plane = ((size_t(P.b[0]) * P.b[1] * P.b[2] + 7) / 8) * 8;
+        smem = size_t(ti.nv4) * plane * 16 + ti.exch_bytes + 16 + 16 * size_t(ti.nwarps);
+        fits = ok && smem <= kMaxSmem;
+    }
+    if (!fits) return false;
     long long tiles = 1;
     for (int k = 0; k < 3; ++k) {
         P.tiles[k] = (P.n[k] + P.t[k] - 1) / P.t[k];
         tiles *= P.tiles[k];
     }
     if (tiles > 0x7fffffffLL) return false;
-    const size_t plane = ((size_t(P.b[0]) * P.b[1] * P.b[2] + 7) / 8) * 8;
-    const size_t smem = size_t(ti.nv4) * plane * 16 + ti.exch_bytes + 16 + 16 * size_t(ti.nwarps);
-    if (smem > kMaxSmem) return false;
     pl->smem = smem;
     pl->threads = ti.nwarps * 32;
     pl->grid = int(tiles);
@@ -296,7 +307,7 @@ extern "C" int ndnlm_plan_create(ndnlm_plan_t** out_plan, const int64_t shape[4]
         pl->elem_bytes = 4;
         pl->padded_bytes = size_t(pvox) * P.nv4 * 16;
         pl->out_bytes = size_t(voxels) * P.nv4 * 16;
-        snprintf(pl->name, sizeof(pl->name), "%s", g_tiled[pl->inst].name);
+        snprintf(pl->name, sizeof(pl->name), "%s[passes=%d]", g_tiled[pl->inst].name, P.npass);
     } else {
         pl->elem_bytes = (dtype == NDNLM_F64) ? 8 : 4;
         pl->padded_bytes = size_t(pvox) * V * pl->elem_bytes;

@@ -34,6 +34,8 @@ struct DevParams {
     int t[3];          // valid tile extent
     int b[3];          // shared-memory box extent
     int tiles[3];      // number of tiles
+    int npass;         // passes over the W search range (each keeps only its rows in shared memory)
+    int ntw_pass;      // W offsets per pass
     float c1, c2;      // w = exp2(-max(D*c1 - c2, 0)),  D = raw patch sum of squared differences
     // generic kernel (double precision constants, reference arithmetic)
     double inv_norm;   // 1 / (V * prod(2f+1))          (nd/_filters.pyx:337)

@@ -239,30 +239,36 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         fence_mbar_init();
     }
     __syncthreads();
-    if (!P.use_ldg_loader) {
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(mbar, uint32_t(NV4) * uint32_t(BW * BRP * BX) * 16u);
+    // The W search range [-rW, rW] is covered in P.npass passes of P.ntw_pass offsets each; a pass keeps
+    // only the rows it needs in shared memory (BW = rows of the CTA + ntw_pass - 1), which is what lets
+    // more warps fit beside the exchange buffer.  Pass `p` starts at padded row w0 + p * ntw_pass.
+    auto load_pass = [&](const int pass) {
+        const int wbase = w0 + pass * P.ntw_pass;
+        if (!P.use_ldg_loader) {
+            if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(mbar, uint32_t(NV4) * uint32_t(BW * BRP * BX) * 16u);
 #pragma unroll
-            for (int q = 0; q < NV4; ++q) tma_load_5d(tile + size_t(q) * plane, &tmap, mbar, 0, r0, x0, w0, q);
+                for (int q = 0; q < NV4; ++q) tma_load_5d(tile + size_t(q) * plane, &tmap, mbar, 0, r0, x0, wbase, q);
+            }
+            mbar_wait(mbar, uint32_t(pass & 1));
+        } else {
+            const int box = BW * BRP * BX;
+            for (int i = threadIdx.x; i < NV4 * box; i += blockDim.x) {
+                const int q = i / box;
+                int rem = i - q * box;
+                const int br = rem % BRP;
+                rem /= BRP;
+                const int bx = rem % BX;
+                const int bw = rem / BX;
+                const int gw = wbase + bw, gr = r0 + br, gx = x0 + bx;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gw < P.pd[0] && gr < P.pd[1] && gx < P.pd[2])
+                    v = padded[((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr];
+                tile[size_t(q) * plane + (bw * BX + bx) * BRP + br] = v;
+            }
+            __syncthreads();
         }
-        mbar_wait(mbar, 0);
-    } else {
-        const int box = BW * BRP * BX;
-        for (int i = threadIdx.x; i < NV4 * box; i += blockDim.x) {
-            const int q = i / box;
-            int rem = i - q * box;
-            const int br = rem % BRP;
-            rem /= BRP;
-            const int bx = rem % BX;
-            const int bw = rem / BX;
-            const int gw = w0 + bw, gr = r0 + br, gx = x0 + bx;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gw < P.pd[0] && gr < P.pd[1] && gx < P.pd[2])
-                v = padded[((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr];
-            tile[size_t(q) * plane + (bw * BX + bx) * BRP + br] = v;
-        }
-        __syncthreads();
-    }
+    };
 
     // ---- warp / lane roles ----
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -270,18 +276,24 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     const int wx = wid % gxw;
     const int wr = (wid / gxw) % grw;
     const int ww = wid / (gxw * grw);
-    const int lw = ww + P.rad[0];               // box coordinates of the centre column
     const int lx = wx * TXW + lane + P.rad[2];
     const int lr0 = wr * L + P.rad[1];
     const bool wvalid = (FW == 0) || (ww >= FW && ww < NWARPS - FW);
 
+    // centre column: read once, straight from the padded cube (R is the fastest axis there too)
     float4 c[NV4][E];
     {
-        const float4* pc = tile + (lw * BX + lx) * BRP + lr0;
+        const int gw = w0 + ww + P.rad[0], gx = x0 + lx;      // padded coordinates of this thread's column
+        const bool inb = gw < P.pd[0] && gx < P.pd[2];
 #pragma unroll
         for (int q = 0; q < NV4; ++q)
 #pragma unroll
-            for (int e = 0; e < E; ++e) c[q][e] = pc[size_t(q) * plane + e];
+            for (int e = 0; e < E; ++e) {
+                const int gr = r0 + lr0 + e;
+                c[q][e] = (inb && gr < P.pd[1])
+                              ? __ldg(padded + ((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
     }
 
     float2 acc_lo[NV4][L], acc_hi[NV4][L];
@@ -433,9 +445,14 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         }
     };
 
-    for (int tw = -rW; tw <= rW; ++tw) {
+    for (int pass = 0; pass < P.npass; ++pass) {
+    const int twa = -rW + pass * P.ntw_pass;
+    const int twb = min(rW, twa + P.ntw_pass - 1);
+    if (pass > 0) __syncthreads();     // every warp is done with the previous pass's rows
+    load_pass(pass);
+    for (int tw = twa; tw <= twb; ++tw) {
         for (int tx = -rX; tx <= rX; ++tx) {
-            const float4* nb0 = tile + ((lw + tw) * BX + lx + tx) * BRP + lr0;
+            const float4* nb0 = tile + ((ww + tw - twa) * BX + lx + tx) * BRP + lr0;
             const bool centre_step = (tw == 0) & (tx == 0);
             for (int ch0 = -rR; ch0 <= rR; ch0 += CH) {
                 const int nj = min(CH, rR - ch0 + 1);                        // uniform
@@ -457,6 +474,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 Q2[o2] = make_float2(0.f, 0.f);
             }
         }
+    }
     }
 
     // ---- epilogue: self weight, normalise, store (nd/_filters.pyx:405-420) ----
