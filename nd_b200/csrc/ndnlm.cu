@@ -15,8 +15,6 @@
 #include "nlm_common.cuh"
 #include "nlm_generic.cuh"
 #include "nlm_staging.cuh"
-#include "nlm_tiled.cuh"
-
 using namespace ndnlm;
 
 // ------------------------------------------------------------------------------------------
@@ -70,26 +68,7 @@ static inline unsigned blocks_for(long long total, int threads) { return unsigne
 // ------------------------------------------------------------------------------------------
 // tiled-kernel instantiation table
 // ------------------------------------------------------------------------------------------
-typedef cudaError_t (*tiled_launch_fn)(const CUtensorMap&, const DevParams&, const float4*, float4*, int*, int grid,
-                                       size_t smem, cudaStream_t);
-
-template <int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
-static cudaError_t launch_tiled(const CUtensorMap& tmap, const DevParams& P, const float4* padded, float4* out,
-                                int* err, int grid, size_t smem, cudaStream_t st) {
-    auto kern = nlm_tiled_kernel<NV4, FW, FX, FR, L, NWARPS, CH, NEFF>;
-    // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
-    static std::atomic<bool> opted_in[64];
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64 || !opted_in[dev].load()) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) opted_in[dev].store(true);
-    }
-    kern<<<grid, NWARPS * 32, smem, st>>>(tmap, P, padded, out, err);
-    return cudaGetLastError();
-}
+#include "nlm_tiled_launch.cuh"
 
 struct TiledInst {
     int nv4, fw, fx, fr, L, nwarps, ch;
@@ -99,17 +78,31 @@ struct TiledInst {
     const char* name;
 };
 
+// The instantiations live in ndnlm_tiled_g*.cu (explicit instantiation definitions); here they are only declared.
+#define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                        \
+    extern template cudaError_t launch_tiled<NV4, FW, FX, FR, L, NW, CH, NEFF>(                               \
+        const CUtensorMap&, const ndnlm::DevParams&, const float4*, float4*, int*, int, size_t, cudaStream_t);
+#include "instances_g0.inc"
+#include "instances_g1.inc"
+#include "instances_g2.inc"
+#include "instances_g3.inc"
+#undef TILED_INST
+
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
     {                                                                                                \
         NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES,     \
             launch_tiled<NV4, FW, FX, FR, L, NW, CH, NEFF>,                                          \
             "nlm_tiled<nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
-    }
+    },
 
 // Candidates are tried in order; the first whose shared-memory box fits is used.
 static const TiledInst g_tiled[] = {
-#include "nlm_tiled_instances.inc"
+#include "instances_g0.inc"
+#include "instances_g1.inc"
+#include "instances_g2.inc"
+#include "instances_g3.inc"
 };
+#undef TILED_INST
 static const int g_ntiled = int(sizeof(g_tiled) / sizeof(g_tiled[0]));
 
 // ------------------------------------------------------------------------------------------

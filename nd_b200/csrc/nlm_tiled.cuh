@@ -199,7 +199,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                  const float4* __restrict__ padded, float4* __restrict__ out, int* __restrict__ err) {
     using Cfg = TiledCfg<NV4, FW, FX, FR, L, NWARPS, CH, NEFF>;
     static_assert(L % 2 == 0, "L must be even (outputs are exchanged in pairs)");
-    constexpr int E = Cfg::E, WN = Cfg::WN, TXW = Cfg::TXW;
+    constexpr int E = Cfg::E, TXW = Cfg::TXW;
 
     // Shared memory: the padded box as [q][BW][BX][BRP] float4 -- R is the FASTEST axis and its
     // pitch BRP is odd, so a thread's column / neighbour window is a run of consecutive float4
@@ -334,7 +334,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         constexpr bool CENTRE = decltype(centre_tag)::value;
         constexpr int WNJ = E + NJ - 1;
         if constexpr (CENTRE && FW > 0) mbar_wait(mbar_empty + wid, xpar ^ 1);
-        float2 own[NDNLM_KEEP_OWN != 0 ? NJ : 1][L / 2];
+        [[maybe_unused]] float2 own[NDNLM_KEEP_OWN != 0 ? NJ : 1][L / 2];
 
         float4 n[NV4][WNJ];
 #pragma unroll
@@ -445,24 +445,10 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         }
     };
 
-    for (int pass = 0; pass < P.npass; ++pass) {
-    const int twa = -rW + pass * P.ntw_pass;
-    const int twb = min(rW, twa + P.ntw_pass - 1);
-    if (pass > 0) __syncthreads();     // every warp is done with the previous pass's rows
-    load_pass(pass);
-    for (int tw = twa; tw <= twb; ++tw) {
-        for (int tx = -rX; tx <= rX; ++tx) {
-            const float4* nb0 = tile + ((ww + tw - twa) * BX + lx + tx) * BRP + lr0;
-            const bool centre_step = (tw == 0) & (tx == 0);
-            for (int ch0 = -rR; ch0 <= rR; ch0 += CH) {
-                const int nj = min(CH, rR - ch0 + 1);                        // uniform
-                const bool centre = centre_step && ch0 <= 0 && ch0 + nj > 0;
-                dispatch_chunk<CH>(nj, centre, [&](auto nj_tag, auto centre_tag) {
-                    chunk(nj_tag, centre_tag, nb0 + ch0, ch0);
-                });
-            }
-        }
-        // fold the fp32 partial weight sums of this W-offset row into float64
+    // The R-offset range [-rR, rR] is cut into chunks of CH; all chunks of a step are full except the last.
+    // When the whole range fits ONE chunk (2 rR + 1 <= CH, e.g. cfg3: 5 offsets) the chunk size is hoisted
+    // out of the offset loops, so the hot loop contains no dispatch at all.
+    auto fold_weight_sums = [&]() {
 #pragma unroll
         for (int o2 = 0; o2 < L / 2; ++o2) {
             Sd[2 * o2] += NDNLM_FOLD_T(S2[o2].x);
@@ -474,7 +460,40 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 Q2[o2] = make_float2(0.f, 0.f);
             }
         }
-    }
+    };
+    const int nR = 2 * rR + 1;
+    for (int pass = 0; pass < P.npass; ++pass) {
+        const int twa = -rW + pass * P.ntw_pass;
+        const int twb = min(rW, twa + P.ntw_pass - 1);
+        if (pass > 0) __syncthreads();     // every warp is done with the previous pass's rows
+        load_pass(pass);
+        if (nR <= CH) {
+            dispatch_chunk<CH>(nR, false, [&](auto nj_tag, auto) {
+                for (int tw = twa; tw <= twb; ++tw) {
+                    for (int tx = -rX; tx <= rX; ++tx) {
+                        const float4* nb0 = tile + ((ww + tw - twa) * BX + lx + tx) * BRP + lr0 - rR;
+                        if ((tw == 0) & (tx == 0)) chunk(nj_tag, std::true_type{}, nb0, -rR);
+                        else chunk(nj_tag, std::false_type{}, nb0, -rR);
+                    }
+                    fold_weight_sums();   // fp32 partial weight sums of this W-offset row -> float64
+                }
+            });
+        } else {
+            for (int tw = twa; tw <= twb; ++tw) {
+                for (int tx = -rX; tx <= rX; ++tx) {
+                    const float4* nb0 = tile + ((ww + tw - twa) * BX + lx + tx) * BRP + lr0;
+                    const bool centre_step = (tw == 0) & (tx == 0);
+                    for (int ch0 = -rR; ch0 <= rR; ch0 += CH) {
+                        const int nj = min(CH, rR - ch0 + 1);                        // uniform
+                        const bool centre = centre_step && ch0 <= 0 && ch0 + nj > 0;
+                        dispatch_chunk<CH>(nj, centre, [&](auto nj_tag, auto centre_tag) {
+                            chunk(nj_tag, centre_tag, nb0 + ch0, ch0);
+                        });
+                    }
+                }
+                fold_weight_sums();
+            }
+        }
     }
 
     // ---- epilogue: self weight, normalise, store (nd/_filters.pyx:405-420) ----

@@ -1,0 +1,27 @@
+// nlm_tiled_launch.cuh -- launcher template of the tiled kernel.  The instantiations are spread over
+// several translation units (ndnlm_tiled_g*.cu, one per instances_g*.inc) so they compile in parallel.
+#pragma once
+#include <atomic>
+
+#include "nlm_tiled.cuh"
+
+typedef cudaError_t (*tiled_launch_fn)(const CUtensorMap&, const ndnlm::DevParams&, const float4*, float4*, int*, int grid,
+                                       size_t smem, cudaStream_t);
+
+template <int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
+cudaError_t launch_tiled(const CUtensorMap& tmap, const ndnlm::DevParams& P, const float4* padded, float4* out,
+                         int* err, int grid, size_t smem, cudaStream_t st) {
+    auto kern = ndnlm::nlm_tiled_kernel<NV4, FW, FX, FR, L, NWARPS, CH, NEFF>;
+    // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
+    static std::atomic<bool> opted_in[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !opted_in[dev].load()) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) opted_in[dev].store(true);
+    }
+    kern<<<grid, NWARPS * 32, smem, st>>>(tmap, P, padded, out, err);
+    return cudaGetLastError();
+}
