@@ -212,8 +212,9 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     uint64_t* mbar =
         reinterpret_cast<uint64_t*>(smem_raw + size_t(NV4) * plane * sizeof(float4) + Cfg::EXCH_BYTES);
     // Neighbour-only synchronisation of the W exchange (no CTA-wide barrier in the hot loop):
-    //   full[w]   warp w's patch sums for the current chunk are in shared memory        (1 arrival)
-    //   empty[w]  every warp that reads warp w's sums has finished with them             (nreaders arrivals)
+    //   full[w]   every row that warp w reads has published its sums for the current chunk (one arrival per
+    //             source row, so a reader waits ONCE)
+    //   empty[w]  every warp that reads warp w's sums has finished with them              (one arrival per reader)
     uint64_t* mbar_full = mbar + 1;
     uint64_t* mbar_empty = mbar + 1 + NWARPS;
 
@@ -232,8 +233,11 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 int readers = 0;   // valid warps within FW rows of w, other than w itself
                 for (int d = -FW; d <= FW; ++d)
                     if (d != 0 && w + d >= FW && w + d < NWARPS - FW) ++readers;
-                mbar_init(mbar_full + w, 1);
-                mbar_init(mbar_empty + w, readers > 0 ? readers : 1);
+                int sources = 0;   // rows within FW of w, other than w itself (the rows w reads)
+                for (int d = -FW; d <= FW; ++d)
+                    if (d != 0 && w + d >= 0 && w + d < NWARPS) ++sources;
+                mbar_init(mbar_full + w, sources);                         // "every row I read is published"
+                mbar_init(mbar_empty + w, readers > 0 ? readers : 1);      // "every reader of my row is done"
             }
         }
         fence_mbar_init();
@@ -323,6 +327,8 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     float2* const ex_own = exch + (wid * (L / 2)) * 32 + lane;     // + (j*NWARPS*(L/2) + o2)*32
     constexpr int EX_J = NWARPS * (L / 2) * 32;                     // float2 stride between R-offsets j
     constexpr int EX_ROW = (L / 2) * 32;                            // float2 stride between W rows (FW>0: 1 warp/row)
+    [[maybe_unused]] float4* const ex_own4 = reinterpret_cast<float4*>(exch) + wid * 32 + lane;   // L == 4 layout
+    [[maybe_unused]] constexpr int EX_J4 = NWARPS * 32;             // float4 stride between R-offsets j
     uint32_t xpar = 0;                                              // parity of the current exchange round
     static_assert(FW == 0 || NWARPS >= 2 * FW + 2, "every row needs at least one reader");
 
@@ -400,10 +406,16 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 if constexpr (!CENTRE) {
                     if (j == 0) mbar_wait(mbar_empty + wid, xpar ^ 1);
                 }
+                if constexpr (L == 4) {
+                    // one 16-B store / load per row and offset: [j][row][lane] float4
+                    ex_own4[j * EX_J4] = make_float4(px[0].x, px[0].y, px[1].x, px[1].y);
+                } else {
 #pragma unroll
-                for (int o2 = 0; o2 < L / 2; ++o2) {
-                    ex_own[j * EX_J + o2 * 32] = px[o2];
-                    if constexpr (NDNLM_KEEP_OWN != 0) own[j][o2] = px[o2];
+                    for (int o2 = 0; o2 < L / 2; ++o2) ex_own[j * EX_J + o2 * 32] = px[o2];
+                }
+                if constexpr (NDNLM_KEEP_OWN != 0) {
+#pragma unroll
+                    for (int o2 = 0; o2 < L / 2; ++o2) own[j][o2] = px[o2];
                 }
             }
         }
@@ -411,34 +423,52 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         // ---- phase B: box sum along W through shared memory, then weights ----
         if constexpr (FW > 0) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(mbar_full + wid);          // release: my sums are published
+            // release: my sums are published -- tell every valid row that reads them (lanes 0..2FW-1, one each)
+            if (lane < 2 * FW) {
+                const int d = (lane < FW) ? lane - FW : lane - FW + 1;
+                if (wid + d >= FW && wid + d < NWARPS - FW) mbar_arrive(mbar_full + wid + d);
+            }
             if (wvalid) {
-#pragma unroll
-                for (int d = -FW; d <= FW; ++d)
-                    if (d != 0) mbar_wait(mbar_full + wid + d, xpar);   // acquire the neighbour rows
+                mbar_wait(mbar_full + wid, xpar);                  // acquire: all rows I read are published
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     if constexpr (CENTRE) {
                         if (ch0 + j == 0) continue;
                     }
                     float2 D[L / 2];
-#pragma unroll
-                    for (int o2 = 0; o2 < L / 2; ++o2) {
-                        float2 t = ex_own[j * EX_J + o2 * 32 - FW * EX_ROW];
+                    if constexpr (L == 4) {
+                        float4 t = ex_own4[j * EX_J4 - FW * 32];
+                        D[0] = make_float2(t.x, t.y);
+                        D[1] = make_float2(t.z, t.w);
 #pragma unroll
                         for (int d = -FW + 1; d <= FW; ++d) {
-                            if (NDNLM_KEEP_OWN != 0 && d == 0) t = __fadd2_rn(t, own[j][o2]);
-                            else t = __fadd2_rn(t, ex_own[j * EX_J + o2 * 32 + d * EX_ROW]);
+                            if (NDNLM_KEEP_OWN != 0 && d == 0) {
+                                D[0] = __fadd2_rn(D[0], own[j][0]);
+                                D[1] = __fadd2_rn(D[1], own[j][1]);
+                            } else {
+                                t = ex_own4[j * EX_J4 + d * 32];
+                                D[0] = __fadd2_rn(D[0], make_float2(t.x, t.y));
+                                D[1] = __fadd2_rn(D[1], make_float2(t.z, t.w));
+                            }
                         }
-                        D[o2] = t;
+                    } else {
+#pragma unroll
+                        for (int o2 = 0; o2 < L / 2; ++o2) {
+                            float2 t = ex_own[j * EX_J + o2 * 32 - FW * EX_ROW];
+#pragma unroll
+                            for (int d = -FW + 1; d <= FW; ++d) {
+                                if (NDNLM_KEEP_OWN != 0 && d == 0) t = __fadd2_rn(t, own[j][o2]);
+                                else t = __fadd2_rn(t, ex_own[j * EX_J + o2 * 32 + d * EX_ROW]);
+                            }
+                            D[o2] = t;
+                        }
                     }
                     weigh(D, j);
                 }
                 __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (int d = -FW; d <= FW; ++d)
-                        if (d != 0) mbar_arrive(mbar_empty + wid + d);   // done reading the neighbour rows
+                if (lane < 2 * FW) {                                  // done reading the neighbour rows
+                    const int d = (lane < FW) ? lane - FW : lane - FW + 1;
+                    mbar_arrive(mbar_empty + wid + d);
                 }
             }
             xpar ^= 1;
