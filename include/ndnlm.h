@@ -57,6 +57,8 @@ extern "C" {
 /* ---- how the two ends of user axis `shard_axis` are padded by ndnlm_stage ---- */
 #define NDNLM_EDGE_REFLECT 0     /* global edge: reflect locally (reference `_idx`, nd/_filters.pyx:34-40) */
 #define NDNLM_EDGE_HALO    1     /* interior shard edge: halo rows are filled by the caller (neighbour exchange) */
+#define NDNLM_EDGE_SOURCE  2     /* slab of a larger array: `arr` has r+f real rows beyond this edge (the `buffer`
+                                    rows of the reference's xr_split, nd/utils.py:288-312); they are read in place */
 
 typedef struct ndnlm_plan ndnlm_plan_t;
 
@@ -103,7 +105,9 @@ int  ndnlm_plan_info(const ndnlm_plan_t* plan, ndnlm_info_t* info);
  * Replaces the per-access `_idx(p+d, N, m)` reflection (nd/_filters.pyx:378-384) by materialising
  * np.pad(mode='reflect') by r+f once.  `shard_axis` (user axis 0..2, or -1) with edge modes lets a
  * y-shard skip reflection on interior edges: with NDNLM_EDGE_HALO those pad rows are left
- * untouched and must be written by the caller via ndnlm_halo_* before ndnlm_run.
+ * untouched and must be written by the caller via ndnlm_halo_* before ndnlm_run; with
+ * NDNLM_EDGE_SOURCE the r+f rows beyond that edge are read from `arr` itself (indices -(r+f)..-1
+ * resp. N..N+r+f-1 along `shard_axis` must be valid memory: `arr` points into a larger array).
  */
 int ndnlm_stage(const ndnlm_plan_t* plan, const void* arr, const int64_t arr_strides[4],
                 void* padded, int shard_axis, int lo_edge, int hi_edge, void* stream);

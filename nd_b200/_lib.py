@@ -15,7 +15,7 @@ OK, EINVAL, EDTYPE, ECUDA, ENOSOLUTION, ERADIUS = 0, -1, -2, -3, -4, -5
 F32, F64 = 0, 1
 AS_WRITTEN, REFERENCE_COMPILED = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED = 0, 1, 2
-EDGE_REFLECT, EDGE_HALO = 0, 1
+EDGE_REFLECT, EDGE_HALO, EDGE_SOURCE = 0, 1, 2
 
 SEMANTICS = {"as_written": AS_WRITTEN, "reference_compiled": REFERENCE_COMPILED}
 KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "tiled": KERNEL_TILED}

@@ -86,6 +86,7 @@ struct TiledInst {
 #include "instances_g1.inc"
 #include "instances_g2.inc"
 #include "instances_g3.inc"
+#include "instances_g4.inc"
 #undef TILED_INST
 
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
@@ -101,6 +102,7 @@ static const TiledInst g_tiled[] = {
 #include "instances_g1.inc"
 #include "instances_g2.inc"
 #include "instances_g3.inc"
+#include "instances_g4.inc"
 };
 #undef TILED_INST
 static const int g_ntiled = int(sizeof(g_tiled) / sizeof(g_tiled[0]));
@@ -161,7 +163,7 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti) {
     const int ntw = 2 * P.rad[0] + 1;
     bool fits = false;
     size_t smem = 0;
-    for (int npass = 1; npass <= 4 && npass <= ntw && !fits; ++npass) {
+    for (int npass = 1; npass <= ntw && !fits; ++npass) {
         const int per = (ntw + npass - 1) / npass;
         P.npass = (ntw + per - 1) / per;
         P.ntw_pass = per;
@@ -379,8 +381,11 @@ extern "C" int ndnlm_stage(const ndnlm_plan_t* pl, const void* arr, const int64_
     if (shard_axis >= 0) {
         if (shard_axis > 2) return fail(NDNLM_EINVAL, "shard_axis must be -1..2");
         S.halo_role = role_of_axis(pl, shard_axis);
-        S.lo_halo = lo_edge == NDNLM_EDGE_HALO;
-        S.hi_halo = hi_edge == NDNLM_EDGE_HALO;
+        if (lo_edge < NDNLM_EDGE_REFLECT || lo_edge > NDNLM_EDGE_SOURCE || hi_edge < NDNLM_EDGE_REFLECT ||
+            hi_edge > NDNLM_EDGE_SOURCE)
+            return fail(NDNLM_EINVAL, "unknown edge mode");
+        S.lo_halo = lo_edge;
+        S.hi_halo = hi_edge;
     }
     const long long pvox = (long long)S.pd[0] * S.pd[1] * S.pd[2];
     if (pl->kernel == NDNLM_KERNEL_TILED) {

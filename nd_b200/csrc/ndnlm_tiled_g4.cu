@@ -1,0 +1,7 @@
+// Explicit instantiations of the tiled kernel, group 4 (instances_g4.inc); see nlm_tiled_launch.cuh.
+#include "nlm_tiled_launch.cuh"
+
+#define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
+    template cudaError_t launch_tiled<NV4, FW, FX, FR, L, NW, CH, NEFF>(                              \
+        const CUtensorMap&, const ndnlm::DevParams&, const float4*, float4*, int*, int, size_t, cudaStream_t);
+#include "instances_g4.inc"

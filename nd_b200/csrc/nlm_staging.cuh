@@ -21,7 +21,8 @@ struct StageParams {
     long long vstride;             // user element stride of the variable axis
     int V, nv4;
     int halo_role;                 // role of the shard axis or -1
-    int lo_halo, hi_halo;          // 1: leave those pad rows untouched
+    int lo_halo, hi_halo;          // edge mode of the shard axis: 0 reflect, 1 leave those pad rows untouched,
+                                   // 2 the source array itself extends over them (slab of a larger array)
 };
 
 template <typename TIN>
@@ -41,8 +42,12 @@ __global__ void stage_tiled_kernel(const StageParams S, const TIN* __restrict__ 
     for (int role = 0; role < 3; ++role) {
         const int u = ip[role] - S.pad[role];
         if (role == S.halo_role) {
-            if (S.lo_halo && u < 0) return;
-            if (S.hi_halo && u >= S.n[role]) return;
+            if (S.lo_halo == 1 && u < 0) return;
+            if (S.hi_halo == 1 && u >= S.n[role]) return;
+            if ((S.lo_halo == 2 && u < 0) || (S.hi_halo == 2 && u >= S.n[role])) {
+                src += (long long)u * S.rstride[role];      // real rows of the enclosing array
+                continue;
+            }
         }
         src += (long long)reflect_index(u, S.n[role]) * S.rstride[role];
     }
@@ -72,8 +77,12 @@ __global__ void stage_generic_kernel(const StageParams S, const T* __restrict__ 
     for (int role = 0; role < 3; ++role) {
         const int u = ip[role] - S.pad[role];
         if (role == S.halo_role) {
-            if (S.lo_halo && u < 0) return;
-            if (S.hi_halo && u >= S.n[role]) return;
+            if (S.lo_halo == 1 && u < 0) return;
+            if (S.hi_halo == 1 && u >= S.n[role]) return;
+            if ((S.lo_halo == 2 && u < 0) || (S.hi_halo == 2 && u >= S.n[role])) {
+                src += (long long)u * S.rstride[role];      // real rows of the enclosing array
+                continue;
+            }
         }
         src += (long long)reflect_index(u, S.n[role]) * S.rstride[role];
     }

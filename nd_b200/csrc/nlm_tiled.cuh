@@ -129,7 +129,8 @@ __device__ __forceinline__ void column_box_sum_paired(const float (&s)[L + 2], f
     }
 }
 
-// Direct (2F+1)-term sum across lanes, fixed order (lane x gets x-F..x+F).
+// (2F+1)-term sum across lanes in a fixed order that depends only on the lane-relative position
+// (lane x gets x-F..x+F).  F == 2 uses pair sums: ((v[x-2]+v[x-1]) + (v[x]+v[x+1])) + v[x+2], 3 shuffles.
 template <int F>
 __device__ __forceinline__ float lane_box_sum(float v) {
     if constexpr (F == 0) {
@@ -138,6 +139,11 @@ __device__ __forceinline__ float lane_box_sum(float v) {
         const float a = __shfl_up_sync(FULL_MASK, v, 1);
         const float b = __shfl_down_sync(FULL_MASK, v, 1);
         return (a + v) + b;
+    } else if constexpr (F == 2) {
+        const float pair = v + __shfl_down_sync(FULL_MASK, v, 1);
+        const float left = __shfl_up_sync(FULL_MASK, pair, 2);
+        const float right = __shfl_down_sync(FULL_MASK, v, 2);
+        return (left + pair) + right;
     } else {
         float t = v;
 #pragma unroll
@@ -166,20 +172,25 @@ __device__ __forceinline__ void dispatch_chunk(const int nj, const bool centre, 
 // The same for two values at once (a register pair): the adds are packed FADD2.
 template <int F>
 __device__ __forceinline__ float2 lane_box_sum2(const float2 v) {
+    auto up = [](const float2 a, const int d) {
+        return make_float2(__shfl_up_sync(FULL_MASK, a.x, d), __shfl_up_sync(FULL_MASK, a.y, d));
+    };
+    auto down = [](const float2 a, const int d) {
+        return make_float2(__shfl_down_sync(FULL_MASK, a.x, d), __shfl_down_sync(FULL_MASK, a.y, d));
+    };
     if constexpr (F == 0) {
         return v;
     } else if constexpr (F == 1) {
-        const float2 a = make_float2(__shfl_up_sync(FULL_MASK, v.x, 1), __shfl_up_sync(FULL_MASK, v.y, 1));
-        const float2 b = make_float2(__shfl_down_sync(FULL_MASK, v.x, 1), __shfl_down_sync(FULL_MASK, v.y, 1));
+        const float2 a = up(v, 1), b = down(v, 1);
         return __fadd2_rn(__fadd2_rn(a, v), b);
+    } else if constexpr (F == 2) {
+        const float2 pair = __fadd2_rn(v, down(v, 1));
+        const float2 left = up(pair, 2), right = down(v, 2);
+        return __fadd2_rn(__fadd2_rn(left, pair), right);
     } else {
         float2 t = v;
 #pragma unroll
-        for (int d = 1; d <= F; ++d) {
-            const float2 a = make_float2(__shfl_up_sync(FULL_MASK, v.x, d), __shfl_up_sync(FULL_MASK, v.y, d));
-            const float2 b = make_float2(__shfl_down_sync(FULL_MASK, v.x, d), __shfl_down_sync(FULL_MASK, v.y, d));
-            t = __fadd2_rn(t, __fadd2_rn(a, b));
-        }
+        for (int d = 1; d <= F; ++d) t = __fadd2_rn(t, __fadd2_rn(up(v, d), down(v, d)));
         return t;
     }
 }

@@ -98,7 +98,7 @@ class Plan:
 
     def stage(self, arr, padded, shard_axis=-1, lo_edge="reflect", hi_edge="reflect"):
         self._check_arr(arr)
-        edge = {"reflect": _lib.EDGE_REFLECT, "halo": _lib.EDGE_HALO}
+        edge = {"reflect": _lib.EDGE_REFLECT, "halo": _lib.EDGE_HALO, "source": _lib.EDGE_SOURCE}
         _lib.check(self._L.ndnlm_stage(self._h, ctypes.c_void_p(arr.data_ptr()), _lib.i64(arr.stride()),
                                        ctypes.c_void_p(padded.data_ptr()), int(shard_axis), edge[lo_edge], edge[hi_edge],
                                        self._stream(padded)))

@@ -32,6 +32,18 @@ class ShardPlan:
                     raise ValueError('shard of %d rows is smaller than the halo r+f=%d; use fewer shards'
                                      % (hi - lo, halo))
 
+    @classmethod
+    def from_rows(cls, n, rows, halo):
+        """Slabs of `rows` rows each (the last one takes the remainder; a remainder too small to carry a halo
+        is merged into the slab before it)."""
+        n, rows, halo = int(n), max(int(rows), int(halo) + 1, 1), int(halo)
+        self = cls(n, 1, halo)
+        starts = list(range(0, n, rows))
+        if len(starts) > 1 and n - starts[-1] < halo + 1:
+            starts.pop()
+        self.ranges = [(lo, starts[k + 1] if k + 1 < len(starts) else n) for k, lo in enumerate(starts)]
+        return self
+
     @property
     def nshards(self):
         return len(self.ranges)

@@ -9,9 +9,9 @@ with double-buffered device slabs,
 
     H2D of slab i+1   |   stage + nlm kernel + unstage of slab i   |   D2H of slab i-1.
 
-Every slab is filtered on its buffered range and only its interior rows are kept, exactly like
-`xr_merge` strips the buffers, so the result equals the unsliced call (the discarded rows are the only
-ones affected by the cut).
+Every slab is copied with its buffer rows, but only its interior is filtered: the buffer rows serve as the
+halo of the staged cube (NDNLM_EDGE_SOURCE), so no voxel is computed twice and the result is bitwise the
+unsliced call (a voxel's arithmetic does not depend on where its slab starts).
 """
 import numpy as np
 import torch
@@ -47,30 +47,42 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
         raise ValueError('apply_host_pipelined needs dense arrays with identical memory layout')
     n0 = arr.shape[0]
     halo = int(r3[0]) + int(f3[0])
-    if slab_rows is None:
-        row_bytes = arr.itemsize * int(np.prod(arr.shape[1:]))
-        slab_rows = max(4 * halo + 16, min(n0, (1 << 30) // max(row_bytes, 1)))      # ~1 GiB per slab
-    nslab = max(1, -(-n0 // slab_rows))
-    sp = ShardPlan(n0, nslab, halo)
     device = torch.device('cuda', torch.cuda.current_device())
     tdtype = torch.float32 if arr.dtype == np.float32 else torch.float64
+    if slab_rows is None:
+        # ~256 MiB per slab: small enough that filling / draining the pipeline (first H2D, last D2H) is a few
+        # milliseconds, a whole number of kernel tiles along axis 0 so that no tile row is partly empty
+        row_bytes = arr.itemsize * int(np.prod(arr.shape[1:]))
+        slab_rows = max(4 * halo + 16, min(n0, (1 << 28) // max(row_bytes, 1)))
+        probe = dev.Plan((min(n0, max(slab_rows, halo + 1)),) + tuple(arr.shape[1:]), r3, f3, sigma, h, n_eff,
+                         semantics=semantics, dtype=arr.dtype, kernel=kernel)
+        if probe.is_tiled:
+            tile0 = int(probe.info.tile[list(probe.info.role_axis).index(0)])
+            if tile0 > 0:
+                slab_rows = max(tile0, slab_rows // tile0 * tile0)
+    sp = ShardPlan.from_rows(n0, slab_rows, halo)
 
     # host views in memory order: hv[outer..., rows, inner...] with every [outer][lo:hi] block contiguous
     k0 = order.index(0)
     hv_in = torch.from_numpy(arr.transpose(order))
     hv_out = torch.from_numpy(output.transpose(order))
     inv = [order.index(a) for a in range(4)]
-    max_rows = max(sp.buffered_range(i)[1] - sp.buffered_range(i)[0] for i in range(sp.nshards))
-    mem_shape = [arr.shape[a] for a in order]
-    mem_shape[k0] = max_rows
-    d_in = [torch.empty(mem_shape, dtype=tdtype, device=device) for _ in range(2)]
-    d_out = [torch.empty(mem_shape, dtype=tdtype, device=device) for _ in range(2)]
+    max_buf = max(sp.buffered_range(i)[1] - sp.buffered_range(i)[0] for i in range(sp.nshards))
+    max_int = max(hi - lo for lo, hi in sp.ranges)
+    in_shape = [arr.shape[a] for a in order]
+    out_shape = list(in_shape)
+    in_shape[k0] = max_buf
+    out_shape[k0] = max_int
+    d_in = [torch.empty(in_shape, dtype=tdtype, device=device) for _ in range(2)]
+    d_out = [torch.empty(out_shape, dtype=tdtype, device=device) for _ in range(2)]
 
+    # One plan per distinct INTERIOR height.  A slab is staged from its buffered rows -- the `buffer` rows
+    # of xr_split are read in place as the halo (NDNLM_EDGE_SOURCE) -- and only its interior is filtered, so
+    # nothing is computed twice (the reference's workers filter the buffer rows too and xr_merge drops them).
     plans = {}
     pad_bytes = out_bytes = 0
-    for i in range(sp.nshards):
-        blo, bhi = sp.buffered_range(i)
-        shape = (bhi - blo,) + tuple(arr.shape[1:])
+    for lo, hi in sp.ranges:
+        shape = (hi - lo,) + tuple(arr.shape[1:])
         if shape not in plans:
             plans[shape] = dev.Plan(shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)
             pad_bytes = max(pad_bytes, plans[shape].padded_bytes)
@@ -106,10 +118,10 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
             s_comp.wait_event(ev_h2d)
             if ev_out_free[b] is not None:
                 s_comp.wait_event(ev_out_free[b])
-            plan = plans[(rows,) + tuple(arr.shape[1:])]
-            a_in = block(d_in[b], 0, rows).permute(inv)          # logical (N0, N1, N2, V) view
-            a_out = block(d_out[b], 0, rows).permute(inv)
-            plan.stage(a_in, padded[b])
+            plan = plans[(hi - lo,) + tuple(arr.shape[1:])]
+            a_in = block(d_in[b], lo - blo, hi - blo).permute(inv)     # logical (rows, N1, N2, V) view of the interior
+            a_out = block(d_out[b], 0, hi - lo).permute(inv)
+            plan.stage(a_in, padded[b], 0, 'reflect' if lo == 0 else 'source', 'reflect' if hi == n0 else 'source')
             plan.run(padded[b], internal[b], flag)
             plan.unstage(internal[b], a_out)
             ev_comp = torch.cuda.Event()
@@ -117,7 +129,7 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
             ev_in_free[b] = ev_comp
         with torch.cuda.stream(s_d2h):
             s_d2h.wait_event(ev_comp)
-            block(hv_out, lo, hi).copy_(block(d_out[b], lo - blo, hi - blo), non_blocking=True)
+            block(hv_out, lo, hi).copy_(block(d_out[b], 0, hi - lo), non_blocking=True)
             ev_d2h = torch.cuda.Event()
             ev_d2h.record(s_d2h)
             ev_out_free[b] = ev_d2h

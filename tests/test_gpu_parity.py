@@ -79,6 +79,9 @@ CASES = [
     ((9, 12, 8, 6), (1, 1, 1), (1, 1, 1)),         # V=6 (cfg5 variable count)
     ((8, 9, 7, 9), (1, 1, 1), (1, 1, 1)),          # V > 8: several passes of the generic kernel
     ((10, 12, 6, 4), (0, 2, 0), (1, 1, 1)),        # patch axes that are not search axes (direct C-ABI use)
+    ((13, 31, 8, 4), (7, 7, 2), (2, 2, 2)),        # cfg4 parameters (tiled f = 2, several W passes)
+    ((14, 29, 9, 6), (10, 10, 3), (2, 2, 2)),      # cfg5 parameters (V = 6, f = 2: two variable groups, one W offset per pass)
+    ((1, 24, 40, 6), (0, 4, 4), (0, 2, 2)),        # 2-D, V = 6, f = 2
 ]
 
 
