@@ -26,6 +26,8 @@ SYMBOLS = [
     "ndnlm_halo_pack", "ndnlm_halo_unpack", "ndnlm_run", "ndnlm_unstage", "ndnlm_workspace_bytes",
     "ndnlm_apply", "ndnlm_synth_cube", "ndnlm_measure_fp32_peak", "ndnlm_launch_count", "ndnlm_last_error", "ndnlm_version",
 ]
+# every symbol include/ndflt.h declares (sibling filters)
+FLT_SYMBOLS = ["ndflt_correlate", "ndflt_correlate1d", "ndflt_launch_count", "ndflt_last_error"]
 
 
 class Info(ctypes.Structure):
@@ -100,6 +102,16 @@ def lib():
     L.ndnlm_last_error.restype = ctypes.c_char_p
     L.ndnlm_version.argtypes = []
     L.ndnlm_version.restype = ctypes.c_char_p
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.ndflt_correlate.argtypes = [vp, vp, i64p, i64p, i64p, ctypes.c_int, dp, i64p, i64p, ctypes.c_int, ctypes.c_double, vp]
+    L.ndflt_correlate.restype = ctypes.c_int
+    L.ndflt_correlate1d.argtypes = [vp, vp, i64p, i64p, i64p, ctypes.c_int, ctypes.c_int, dp, ctypes.c_int64,
+                                    ctypes.c_int64, ctypes.c_int, ctypes.c_double, vp]
+    L.ndflt_correlate1d.restype = ctypes.c_int
+    L.ndflt_launch_count.argtypes = []
+    L.ndflt_launch_count.restype = ctypes.c_int64
+    L.ndflt_last_error.argtypes = []
+    L.ndflt_last_error.restype = ctypes.c_char_p
     _lib = L
     return L
 

@@ -1,0 +1,338 @@
+// ndflt.cu -- C ABI (include/ndflt.h) of the sibling filters: N-D and 1-D correlation kernels that restate
+// scipy.ndimage's NI_Correlate / NI_Correlate1D operation by operation (see the header for the algorithm and
+// the reference call sites nd/filters.py:260-268 and :370-378).  HBM-bound streaming kernels: one thread per
+// output element, threads run along the axis with the smallest output stride (coalesced stores), neighbours
+// come through L1/L2; an interior fast path skips the boundary-extension index math.
+#include "../../include/ndflt.h"
+#include "../../include/ndnlm.h"
+
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+static thread_local char g_flt_err[512] = "";
+static std::atomic<long long> g_flt_launches{0};
+
+static int flt_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_flt_err, sizeof(g_flt_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define FLT_CUDA_TRY(expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return flt_fail(NDNLM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// The library carries its own static CUDA runtime: bind the device that owns the buffers (see ndnlm.cu).
+struct FltDeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit FltDeviceGuard(const void* ptr) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            ok = false;
+            return;
+        }
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != attr.device && cudaSetDevice(attr.device) != cudaSuccess) ok = false;
+        if (prev == attr.device) prev = -1;
+    }
+    ~FltDeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+namespace ndflt {
+
+// NI_ExtendLine (scipy ni_support.c): index of the element that position i (outside [0, n)) stands for;
+// -1 = the constant `cval`.
+__host__ __device__ inline long long extend_index(long long i, long long n, int mode) {
+    if (i >= 0 && i < n) return i;
+    switch (mode) {
+        case NDFLT_MODE_REFLECT: {           // d c b a | a b c d | d c b a
+            if (n <= 1) return 0;
+            const long long p = 2 * n;
+            long long m = i % p;
+            if (m < 0) m += p;
+            return m < n ? m : p - 1 - m;
+        }
+        case NDFLT_MODE_MIRROR: {            // d c b | a b c d | c b a
+            if (n <= 1) return 0;
+            const long long p = 2 * n - 2;
+            long long m = i % p;
+            if (m < 0) m += p;
+            return m < n ? m : p - m;
+        }
+        case NDFLT_MODE_WRAP: {              // a b c d | a b c d | a b c d
+            if (n <= 1) return 0;
+            long long m = i % n;
+            if (m < 0) m += n;
+            return m;
+        }
+        case NDFLT_MODE_NEAREST:
+            return i < 0 ? 0 : n - 1;
+        default:
+            return -1;
+    }
+}
+
+struct Geometry {
+    long long shape[4], istr[4], ostr[4];
+    int ord[4];            // axes from the fastest-running thread index to the slowest
+    long long total;
+    int mode;
+    double cval;
+};
+
+__device__ __forceinline__ void decompose(const Geometry& G, long long lin, long long (&idx)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int a = G.ord[k];
+        const long long n = G.shape[a];
+        idx[a] = lin % n;
+        lin /= n;
+    }
+}
+
+struct Tap {
+    int off[4];            // offset of the tap from the output position, per axis
+    long long lin;         // the same as an element offset in the input (interior fast path)
+    double w;
+};
+
+// ---- N-D correlation (NI_Correlate) ----------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+correlate_nd_kernel(const Geometry G, const T* __restrict__ in, T* __restrict__ out, const Tap* __restrict__ taps,
+                    const int ntaps, const int4 omin, const int4 omax) {
+    const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lin >= G.total) return;
+    long long idx[4];
+    decompose(G, lin, idx);
+    const int lo[4] = {omin.x, omin.y, omin.z, omin.w}, hi[4] = {omax.x, omax.y, omax.z, omax.w};
+    bool interior = true;
+    long long base = 0, obase = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        interior = interior && (idx[a] + lo[a] >= 0) && (idx[a] + hi[a] < G.shape[a]);
+        base += idx[a] * G.istr[a];
+        obase += idx[a] * G.ostr[a];
+    }
+    double tmp = 0.0;
+    if (interior) {
+        for (int t = 0; t < ntaps; ++t) {
+            const double v = double(__ldg(in + base + __ldg(&taps[t].lin)));
+            tmp = __dadd_rn(tmp, __dmul_rn(v, __ldg(&taps[t].w)));
+        }
+    } else {
+        for (int t = 0; t < ntaps; ++t) {
+            long long src = 0;
+            bool inside = true;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const long long j = extend_index(idx[a] + taps[t].off[a], G.shape[a], G.mode);
+                inside = inside && j >= 0;
+                src += j * G.istr[a];
+            }
+            const double v = inside ? double(__ldg(in + src)) : G.cval;
+            tmp = __dadd_rn(tmp, __dmul_rn(v, __ldg(&taps[t].w)));
+        }
+    }
+    out[obase] = T(tmp);
+}
+
+// ---- 1-D correlation (NI_Correlate1D) ---------------------------------------------------------------
+// SYM: 1 symmetric, -1 antisymmetric, 0 general.  w points at the kernel centre (w[-size1 .. size2]).
+template <typename T, int SYM>
+__global__ void __launch_bounds__(256)
+correlate_1d_kernel(const Geometry G, const T* __restrict__ in, T* __restrict__ out, const double* __restrict__ wbuf,
+                    const int axis, const int size1, const int size2, const int origin) {
+    const long long lin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lin >= G.total) return;
+    long long idx[4];
+    decompose(G, lin, idx);
+    long long base = 0, obase = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        base += idx[a] * G.istr[a];
+        obase += idx[a] * G.ostr[a];
+    }
+    const long long n = G.shape[axis], st = G.istr[axis];
+    const long long l = idx[axis] - origin;               // tap j reads position l + j
+    const T* line = in + (base - idx[axis] * st);           // element 0 of this line
+    const double* w = wbuf + size1;
+    const bool interior = (l - size1 >= 0) && (l + size2 < n);
+    auto at = [&](const int j) -> double {
+        if (interior) return double(__ldg(line + (l + j) * st));
+        const long long k = extend_index(l + j, n, G.mode);
+        return k >= 0 ? double(__ldg(line + k * st)) : G.cval;
+    };
+    double tmp;
+    if (SYM != 0) {
+        tmp = __dmul_rn(at(0), __ldg(w));
+        for (int j = -size1; j < 0; ++j) {
+            const double a = at(j), b = at(-j);
+            const double s = SYM > 0 ? __dadd_rn(a, b) : __dsub_rn(a, b);
+            tmp = __dadd_rn(tmp, __dmul_rn(s, __ldg(w + j)));
+        }
+    } else {
+        tmp = __dmul_rn(at(size2), __ldg(w + size2));
+        for (int j = -size1; j < size2; ++j) tmp = __dadd_rn(tmp, __dmul_rn(at(j), __ldg(w + j)));
+    }
+    out[obase] = T(tmp);
+}
+
+}  // namespace ndflt
+using namespace ndflt;
+
+static int fill_geometry(Geometry& G, const int64_t shape[4], const int64_t in_strides[4], const int64_t out_strides[4],
+                         int mode, double cval) {
+    G.total = 1;
+    for (int a = 0; a < 4; ++a) {
+        if (shape[a] < 1 || shape[a] > 0x7fffffffLL) return flt_fail(NDNLM_EINVAL, "shape[%d]=%lld out of range", a, (long long)shape[a]);
+        G.shape[a] = shape[a];
+        G.istr[a] = in_strides[a];
+        G.ostr[a] = out_strides[a];
+        G.total *= shape[a];
+    }
+    if (mode < NDFLT_MODE_REFLECT || mode > NDFLT_MODE_WRAP) return flt_fail(NDNLM_EINVAL, "unknown boundary mode %d", mode);
+    G.mode = mode;
+    G.cval = cval;
+    // thread order: smallest output stride first (extent-1 axes last)
+    int ax[4] = {0, 1, 2, 3};
+    for (int i = 0; i < 4; ++i)
+        for (int j = i + 1; j < 4; ++j) {
+            auto key = [&](int a) { return shape[a] == 1 ? (long long)0x7fffffffffffffffLL : llabs((long long)out_strides[a]); };
+            if (key(ax[j]) < key(ax[i]) || (key(ax[j]) == key(ax[i]) && ax[j] > ax[i])) {
+                const int t = ax[i]; ax[i] = ax[j]; ax[j] = t;
+            }
+        }
+    for (int k = 0; k < 4; ++k) G.ord[k] = ax[k];
+    return NDNLM_OK;
+}
+
+static inline unsigned flt_blocks(long long total) { return unsigned((total + 255) / 256); }
+
+extern "C" int ndflt_correlate(const void* in, void* out, const int64_t shape[4], const int64_t in_strides[4],
+                               const int64_t out_strides[4], int dtype, const double* weights, const int64_t kshape[4],
+                               const int64_t origin[4], int mode, double cval, void* stream) {
+    if (!in || !out || !shape || !in_strides || !out_strides || !weights || !kshape || !origin)
+        return flt_fail(NDNLM_EINVAL, "null argument");
+    if (dtype != NDFLT_F32 && dtype != NDFLT_F64) return flt_fail(NDNLM_EDTYPE, "only float32 / float64 data is supported");
+    FltDeviceGuard guard(out);
+    if (!guard.ok) return flt_fail(NDNLM_EINVAL, "out is not a CUDA device pointer");
+    Geometry G;
+    int rc = fill_geometry(G, shape, in_strides, out_strides, mode, cval);
+    if (rc) return rc;
+    long long ksz = 1;
+    for (int a = 0; a < 4; ++a) {
+        if (kshape[a] < 1 || kshape[a] > 4096) return flt_fail(NDNLM_EINVAL, "kernel shape[%d]=%lld out of range", a, (long long)kshape[a]);
+        // scipy `_invalid_origin`: -(lenw // 2) <= origin <= (lenw - 1) // 2
+        if (origin[a] < -(kshape[a] / 2) || origin[a] > (kshape[a] - 1) / 2)
+            return flt_fail(NDNLM_EINVAL, "Invalid origin; origin must satisfy -(weights.shape[k] // 2) <= origin[k] <= (weights.shape[k]-1) // 2");
+        ksz *= kshape[a];
+    }
+    if (ksz > (1 << 22)) return flt_fail(NDNLM_EINVAL, "kernel too large");
+    std::vector<Tap> taps;
+    int lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    long long k = 0;
+    for (long long k0 = 0; k0 < kshape[0]; ++k0)
+        for (long long k1 = 0; k1 < kshape[1]; ++k1)
+            for (long long k2 = 0; k2 < kshape[2]; ++k2)
+                for (long long k3 = 0; k3 < kshape[3]; ++k3, ++k) {
+                    const double w = weights[k];
+                    if (!(fabs(w) > DBL_EPSILON)) continue;      // NI_Correlate keeps only the footprint |w| > eps
+                    Tap t;
+                    const long long kk[4] = {k0, k1, k2, k3};
+                    t.lin = 0;
+                    const bool first = taps.empty();
+                    for (int a = 0; a < 4; ++a) {
+                        t.off[a] = int(kk[a] - kshape[a] / 2 - origin[a]);
+                        t.lin += (long long)t.off[a] * in_strides[a];
+                        lo[a] = first ? t.off[a] : (t.off[a] < lo[a] ? t.off[a] : lo[a]);
+                        hi[a] = first ? t.off[a] : (t.off[a] > hi[a] ? t.off[a] : hi[a]);
+                    }
+                    t.w = w;
+                    taps.push_back(t);
+                }
+    cudaStream_t st = (cudaStream_t)stream;
+    Tap* dtaps = nullptr;
+    const size_t nb = (taps.empty() ? 1 : taps.size()) * sizeof(Tap);
+    FLT_CUDA_TRY(cudaMallocAsync((void**)&dtaps, nb, st));
+    if (!taps.empty()) FLT_CUDA_TRY(cudaMemcpyAsync(dtaps, taps.data(), taps.size() * sizeof(Tap), cudaMemcpyHostToDevice, st));
+    // (pageable source: cudaMemcpyAsync returns once the host buffer has been staged, so `taps` may go out of scope)
+    const int4 omin = make_int4(lo[0], lo[1], lo[2], lo[3]), omax = make_int4(hi[0], hi[1], hi[2], hi[3]);
+    if (dtype == NDFLT_F64)
+        correlate_nd_kernel<double><<<flt_blocks(G.total), 256, 0, st>>>(G, (const double*)in, (double*)out, dtaps, int(taps.size()), omin, omax);
+    else
+        correlate_nd_kernel<float><<<flt_blocks(G.total), 256, 0, st>>>(G, (const float*)in, (float*)out, dtaps, int(taps.size()), omin, omax);
+    g_flt_launches++;
+    FLT_CUDA_TRY(cudaGetLastError());
+    FLT_CUDA_TRY(cudaFreeAsync(dtaps, st));
+    return NDNLM_OK;
+}
+
+template <typename T>
+static void launch_1d(int sym, const Geometry& G, const void* in, void* out, const double* dw, int axis, int size1, int size2,
+                      int origin, cudaStream_t st) {
+    const unsigned nb = flt_blocks(G.total);
+    if (sym > 0)
+        correlate_1d_kernel<T, 1><<<nb, 256, 0, st>>>(G, (const T*)in, (T*)out, dw, axis, size1, size2, origin);
+    else if (sym < 0)
+        correlate_1d_kernel<T, -1><<<nb, 256, 0, st>>>(G, (const T*)in, (T*)out, dw, axis, size1, size2, origin);
+    else
+        correlate_1d_kernel<T, 0><<<nb, 256, 0, st>>>(G, (const T*)in, (T*)out, dw, axis, size1, size2, origin);
+}
+
+extern "C" int ndflt_correlate1d(const void* in, void* out, const int64_t shape[4], const int64_t in_strides[4],
+                                 const int64_t out_strides[4], int dtype, int axis, const double* weights,
+                                 int64_t nweights, int64_t origin, int mode, double cval, void* stream) {
+    if (!in || !out || !shape || !in_strides || !out_strides || !weights) return flt_fail(NDNLM_EINVAL, "null argument");
+    if (dtype != NDFLT_F32 && dtype != NDFLT_F64) return flt_fail(NDNLM_EDTYPE, "only float32 / float64 data is supported");
+    if (axis < 0 || axis > 3) return flt_fail(NDNLM_EINVAL, "axis must be 0..3");
+    if (nweights < 1 || nweights > (1 << 20)) return flt_fail(NDNLM_EINVAL, "no filter weights given");
+    if (origin < -(nweights / 2) || origin > (nweights - 1) / 2)
+        return flt_fail(NDNLM_EINVAL, "Invalid origin; origin must satisfy -(len(weights) // 2) <= origin <= (len(weights)-1) // 2");
+    FltDeviceGuard guard(out);
+    if (!guard.ok) return flt_fail(NDNLM_EINVAL, "out is not a CUDA device pointer");
+    Geometry G;
+    int rc = fill_geometry(G, shape, in_strides, out_strides, mode, cval);
+    if (rc) return rc;
+    const int size1 = int(nweights / 2), size2 = int(nweights - size1 - 1);
+    // symmetry test of NI_Correlate1D
+    int sym = 0;
+    if (nweights & 1) {
+        sym = 1;
+        for (int i = 1; i <= size1; ++i)
+            if (fabs(weights[i + size1] - weights[size1 - i]) > DBL_EPSILON) { sym = 0; break; }
+        if (sym == 0) {
+            sym = -1;
+            for (int i = 1; i <= size1; ++i)
+                if (fabs(weights[size1 + i] + weights[size1 - i]) > DBL_EPSILON) { sym = 0; break; }
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double* dw = nullptr;
+    FLT_CUDA_TRY(cudaMallocAsync((void**)&dw, size_t(nweights) * sizeof(double), st));
+    FLT_CUDA_TRY(cudaMemcpyAsync(dw, weights, size_t(nweights) * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (dtype == NDFLT_F64) launch_1d<double>(sym, G, in, out, dw, axis, size1, size2, int(origin), st);
+    else launch_1d<float>(sym, G, in, out, dw, axis, size1, size2, int(origin), st);
+    g_flt_launches++;
+    FLT_CUDA_TRY(cudaGetLastError());
+    FLT_CUDA_TRY(cudaFreeAsync(dw, st));
+    return NDNLM_OK;
+}
+
+extern "C" int64_t ndflt_launch_count(void) { return g_flt_launches.load(); }
+extern "C" const char* ndflt_last_error(void) { return g_flt_err; }

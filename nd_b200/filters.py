@@ -1,5 +1,7 @@
 """
-`Filter` / `NLMeansFilter`, mirroring reference nd/filters.py:82-198 and :388-466.
+`Filter` / `NLMeansFilter`, mirroring reference nd/filters.py:82-198 and :388-466, and the sibling filters
+`ConvolutionFilter` / `BoxcarFilter` / `GaussianFilter` (nd/filters.py:205-381), whose
+scipy.ndimage calls are replaced by the CUDA kernels behind `nd_b200._ndimage`.
 
 Same public surface: `NLMeansFilter(dims, r, sigma, h, f, n_eff).apply(ds, inplace=False, njobs=1)`
 takes and returns a Dataset with the same dims, coords and attrs; the filter plugs in through
@@ -18,6 +20,7 @@ import numpy as np
 
 from .algorithm import Algorithm, parallelize, wrap_algorithm
 from ._filters import _pixelwise_nlmeans_3d
+from . import _ndimage as snf          # GPU stand-in for `scipy.ndimage.filters` (same call signatures)
 
 
 # ---- helpers restated from nd/utils.py:450-524 and nd/io.py:26-123 ---------------------------
@@ -65,6 +68,38 @@ def assemble_complex(ds):
             ds[stem] = (re_v.dims, re_v.values + im_v.values * 1j)
             del ds[parts['re']]
             del ds[parts['im']]
+
+
+def _expand_kernel(kernel, kernel_dims, new_dims):
+    """
+    Reshape a kernel spanning some dimensions to cover a superset of dimensions
+    (reference nd/filters.py:36-75).
+    """
+    if not set(new_dims).issuperset(set(kernel_dims)):
+        raise ValueError('`new_dims` must be a superset of `kernel_dims`.')
+    if kernel.ndim != len(kernel_dims):
+        raise ValueError('The length of `kernel_dims` must match the dimension of `kernel`.')
+    new_kernel_shape = np.ones(len(new_dims), dtype=int)
+    new_kernel_shape[[new_dims.index(_) for _ in kernel_dims]] = kernel.shape
+    return kernel.reshape(new_kernel_shape)
+
+
+def _dim_sizes(ds):
+    sizes = {}
+    if _is_dataarray(ds):
+        return dict(zip(ds.dims, ds.values.shape))
+    for v in ds.data_vars:
+        for d, n in zip(ds[v].dims, ds[v].values.shape):
+            sizes[d] = n
+    return sizes
+
+
+def _largest_extra_dimension(ds, dims):
+    """Largest dimension that is not filtered, else the largest dimension (nd/filters.py:232-243, :345-356)."""
+    sizes = _dim_sizes(ds)
+    extra = [d for d in sizes if d not in dims]
+    pool = extra if extra else list(sizes)
+    return sorted(pool, key=lambda d: sizes[d], reverse=True)[0]
 
 
 class Filter(Algorithm):
@@ -163,6 +198,124 @@ class Filter(Algorithm):
     def _filter(self, arr, axes, output=None):
         """This method must be implemented by all derived classes."""
         return
+
+
+# ------------------------------------------------------------------------------------------------
+# Sibling filters (reference nd/filters.py:205-381).  Same classes, attributes and `_filter` bodies; `snf`
+# is nd_b200._ndimage, whose `convolve` / `gaussian_filter` run on the GPU and match scipy bit for bit.
+# ------------------------------------------------------------------------------------------------
+class ConvolutionFilter(Filter):
+    """
+    Kernel-convolution of a Dataset (reference nd/filters.py:205-268).
+
+    Parameters
+    ----------
+    dims : tuple, optional
+        The dataset dimensions corresponding to the kernel axes (default: ('y', 'x')).
+    kernel : ndarray
+        The convolution kernel.
+    kwargs : dict, optional
+        Extra keyword arguments with the meaning of ``scipy.ndimage.convolve`` (mode, cval, origin).
+    """
+
+    per_variable = True
+    supports_complex = True
+    kwargs = {}
+
+    def __init__(self, dims=('y', 'x'), kernel=None, **kwargs):
+        if kernel is None:
+            kernel = np.ones([1] * len(dims))
+        self.dims = tuple(dims)
+        self.kernel = kernel
+        self.kwargs = kwargs
+
+    def _parallel_dimension(self, ds):
+        return _largest_extra_dimension(ds, self.dims)
+
+    def _buffer(self, dim):
+        if dim not in self.dims:
+            return 0
+        axis = self.dims.index(dim)
+        return self.kernel.shape[axis] // 2
+
+    def _filter(self, arr, axes, output):
+        # Reshape kernel to match dimension of input array (a reshape, not a transpose: nd/filters.py:256-259).
+        new_kernel_shape = np.ones(arr.ndim, dtype=int)
+        new_kernel_shape[list(axes)] = self.kernel.shape
+        nd_kernel = self.kernel.reshape(new_kernel_shape)
+        if np.iscomplexobj(arr):
+            snf.convolve(np.real(arr), nd_kernel, output=np.real(output), **self.kwargs)
+            snf.convolve(np.imag(arr), nd_kernel, output=np.imag(output), **self.kwargs)
+        else:
+            snf.convolve(arr, nd_kernel, output=output, **self.kwargs)
+
+
+convolution = wrap_algorithm(ConvolutionFilter, 'convolution')
+
+
+class BoxcarFilter(ConvolutionFilter):
+    """
+    A boxcar filter of odd width `w` along `dims` (reference nd/filters.py:277-301).
+    """
+
+    def __init__(self, dims=('y', 'x'), w=3, **kwargs):
+        N = len(dims)
+        self.dims = tuple(dims)
+        self.kernel = np.ones((w,) * N, dtype=np.float64) / w**N
+        self.kwargs = kwargs
+
+
+boxcar = wrap_algorithm(BoxcarFilter, 'boxcar')
+
+
+class GaussianFilter(Filter):
+    """
+    A Gaussian filter (reference nd/filters.py:310-378).
+
+    Parameters
+    ----------
+    dims : tuple of str, optional
+        The dimensions along which to apply the Gaussian filtering (default: ('y', 'x')).
+    sigma : float or sequence of float
+        The standard deviation for the Gaussian kernel, per dimension if a sequence.
+    kwargs : dict, optional
+        Extra keyword arguments with the meaning of ``scipy.ndimage.gaussian_filter``.
+    """
+
+    def __init__(self, dims=('y', 'x'), sigma=1, **kwargs):
+        if isinstance(sigma, (int, float)):
+            sigma = [sigma] * len(dims)
+        self.dims = tuple(dims)
+        self.sigma = sigma
+        self.kwargs = kwargs
+
+    def _parallel_dimension(self, ds):
+        return _largest_extra_dimension(ds, self.dims)
+
+    def _buffer(self, dim):
+        if dim not in self.dims:
+            return 0
+        # the kernel is truncated after 4 sigma by default (nd/filters.py:362-368)
+        axis = self.dims.index(dim)
+        sigma = self.sigma[axis]
+        truncate = 4.0
+        return int(truncate * sigma + 0.5)
+
+    def _filter(self, arr, axes, output):
+        # Generate n-dimensional sigma
+        ndsigma = [0] * arr.ndim
+        for ax, s in zip(axes, self.sigma):
+            ndsigma[ax] = s
+        if np.iscomplexobj(arr):
+            # (unreachable through `apply`: supports_complex is False; kept as in the reference, including
+            #  its write of the imaginary part into np.real(output), nd/filters.py:373-376)
+            snf.gaussian_filter(np.real(arr), sigma=ndsigma, output=np.real(output), **self.kwargs)
+            snf.gaussian_filter(np.imag(arr), sigma=ndsigma, output=np.real(output), **self.kwargs)
+        else:
+            snf.gaussian_filter(arr, sigma=ndsigma, output=output, **self.kwargs)
+
+
+gaussian = wrap_algorithm(GaussianFilter, 'gaussian')
 
 
 class NLMeansFilter(Filter):
