@@ -56,12 +56,15 @@ struct FltDeviceGuard {
 namespace ndflt {
 
 // NI_ExtendLine (scipy ni_support.c): index of the element that position i (outside [0, n)) stands for;
-// -1 = the constant `cval`.
+// -1 = the constant `cval`.  One reflection / wrap covers every kernel that is not longer than the axis; only
+// longer kernels take the modulo path.
 __host__ __device__ inline long long extend_index(long long i, long long n, int mode) {
     if (i >= 0 && i < n) return i;
     switch (mode) {
         case NDFLT_MODE_REFLECT: {           // d c b a | a b c d | d c b a
             if (n <= 1) return 0;
+            const long long once = i < 0 ? -i - 1 : 2 * n - 1 - i;
+            if (once >= 0 && once < n) return once;
             const long long p = 2 * n;
             long long m = i % p;
             if (m < 0) m += p;
@@ -69,6 +72,8 @@ __host__ __device__ inline long long extend_index(long long i, long long n, int 
         }
         case NDFLT_MODE_MIRROR: {            // d c b | a b c d | c b a
             if (n <= 1) return 0;
+            const long long once = i < 0 ? -i : 2 * n - 2 - i;
+            if (once >= 0 && once < n) return once;
             const long long p = 2 * n - 2;
             long long m = i % p;
             if (m < 0) m += p;
@@ -76,6 +81,8 @@ __host__ __device__ inline long long extend_index(long long i, long long n, int 
         }
         case NDFLT_MODE_WRAP: {              // a b c d | a b c d | a b c d
             if (n <= 1) return 0;
+            const long long once = i < 0 ? i + n : i - n;
+            if (once >= 0 && once < n) return once;
             long long m = i % n;
             if (m < 0) m += n;
             return m;
@@ -96,6 +103,18 @@ struct Geometry {
 };
 
 __device__ __forceinline__ void decompose(const Geometry& G, long long lin, long long (&idx)[4]) {
+    if (G.total <= 0xffffffffLL) {          // 32-bit divisions are several times cheaper than 64-bit ones
+        unsigned l = unsigned(lin);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int a = G.ord[k];
+            const unsigned n = unsigned(G.shape[a]);
+            const unsigned q = l / n;
+            idx[a] = l - q * n;
+            l = q;
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int a = G.ord[k];
@@ -194,7 +213,40 @@ correlate_1d_kernel(const Geometry G, const T* __restrict__ in, T* __restrict__ 
 }
 
 }  // namespace ndflt
+#include "ndflt_tiled.cuh"
 using namespace ndflt;
+
+// C-contiguous (row-major) layout of both arrays?  (extent-1 axes may carry any stride)
+static bool is_contiguous(const int64_t shape[4], const int64_t strides[4]) {
+    long long expect = 1;
+    for (int a = 3; a >= 0; --a) {
+        if (shape[a] != 1 && strides[a] != expect) return false;
+        expect *= shape[a];
+    }
+    return true;
+}
+
+// Tile geometry of the [outer][n][inner] view around axis `s`; false if the grid would not fit.
+static bool make_tile(TileGeom& T, const int64_t shape[4], int s, int taps_along_s, int mode, double cval) {
+    T.outer = 1;
+    T.inner = 1;
+    for (int a = 0; a < s; ++a) T.outer *= shape[a];
+    for (int a = s + 1; a < 4; ++a) T.inner *= shape[a];
+    T.n = shape[s];
+    if (T.inner > 0xffffffffLL) return false;
+    T.TI = int(T.inner < TILE_THREADS ? T.inner : TILE_THREADS);
+    T.RP = TILE_THREADS / T.TI;
+    int rows = 4 * taps_along_s;                       // rows per CTA: re-read overhead (rows + taps) / rows
+    rows = rows < 16 ? 16 : (rows > 64 ? 64 : rows);
+    T.U = (rows + T.RP - 1) / T.RP;
+    const long long nbi = (T.inner + T.TI - 1) / T.TI, nbn = (T.n + (long long)T.RP * T.U - 1) / ((long long)T.RP * T.U);
+    if (nbi * nbn * T.outer > 0x7fffffffLL) return false;
+    T.nbi = unsigned(nbi);
+    T.nbn = unsigned(nbn);
+    T.mode = mode;
+    T.cval = cval;
+    return true;
+}
 
 static int fill_geometry(Geometry& G, const int64_t shape[4], const int64_t in_strides[4], const int64_t out_strides[4],
                          int mode, double cval) {
@@ -223,6 +275,41 @@ static int fill_geometry(Geometry& G, const int64_t shape[4], const int64_t in_s
 }
 
 static inline unsigned flt_blocks(long long total) { return unsigned((total + 255) / 256); }
+
+// Dense 2-D footprints: instantiations for 3x3, 3x5, 5x3, 5x5, 7x7 (U = 16 consecutive rows per thread).
+constexpr int DENSE_U = 16;
+template <typename T, int KH, int KW>
+static int launch_dense2d_t(const TileGeom& TG, const Dense2dGeom& D, const void* in, void* out, const double* weights,
+                            cudaStream_t st) {
+    TileGeom G = TG;
+    G.U = DENSE_U;
+    const long long nbn = (G.n + (long long)G.RP * DENSE_U - 1) / ((long long)G.RP * DENSE_U);
+    if (G.outer * nbn * G.nbi > 0x7fffffffLL) return 1;
+    G.nbn = unsigned(nbn);
+    double* dw = nullptr;
+    FLT_CUDA_TRY(cudaMallocAsync((void**)&dw, sizeof(double) * KH * KW, st));
+    FLT_CUDA_TRY(cudaMemcpyAsync(dw, weights, sizeof(double) * KH * KW, cudaMemcpyHostToDevice, st));
+    correlate_2d_slide_kernel<T, KH, KW, DENSE_U><<<unsigned(G.outer * G.nbn * G.nbi), TILE_THREADS, 0, st>>>(
+        G, D, (const T*)in, (T*)out, dw);
+    g_flt_launches++;
+    FLT_CUDA_TRY(cudaGetLastError());
+    FLT_CUDA_TRY(cudaFreeAsync(dw, st));
+    return NDNLM_OK;
+}
+static int launch_dense2d(int dtype, int kh, int kw, const TileGeom& TG, const Dense2dGeom& D, const void* in, void* out,
+                          const double* weights, cudaStream_t st) {
+#define NDFLT_DENSE(KH, KW)                                                                             \
+    if (kh == KH && kw == KW)                                                                           \
+        return dtype == NDFLT_F64 ? launch_dense2d_t<double, KH, KW>(TG, D, in, out, weights, st)       \
+                                  : launch_dense2d_t<float, KH, KW>(TG, D, in, out, weights, st);
+    NDFLT_DENSE(3, 3)
+    NDFLT_DENSE(3, 5)
+    NDFLT_DENSE(5, 3)
+    NDFLT_DENSE(5, 5)
+    NDFLT_DENSE(7, 7)
+#undef NDFLT_DENSE
+    return 1;
+}
 
 extern "C" int ndflt_correlate(const void* in, void* out, const int64_t shape[4], const int64_t in_strides[4],
                                const int64_t out_strides[4], int dtype, const double* weights, const int64_t kshape[4],
@@ -267,6 +354,70 @@ extern "C" int ndflt_correlate(const void* in, void* out, const int64_t shape[4]
                     taps.push_back(t);
                 }
     cudaStream_t st = (cudaStream_t)stream;
+    // ---- fast path: contiguous arrays, footprint small enough for shared memory ----
+    int s_axis = 3;
+    for (int a = 3; a >= 0; --a)
+        if (kshape[a] > 1) s_axis = a;
+    TileGeom TG;
+    // ---- fastest path: dense KH x KW footprint over the tiled axis and ONE trailing axis ----
+    {
+        int x_axis = -1, nk = 0;
+        for (int a = 0; a < 4; ++a)
+            if (kshape[a] > 1) { ++nk; if (a != s_axis) x_axis = a; }
+        const bool dense = (long long)taps.size() == ksz;
+        if (dense && nk == 2 && x_axis > s_axis && is_contiguous(shape, in_strides) && is_contiguous(shape, out_strides) &&
+            make_tile(TG, shape, s_axis, int(kshape[s_axis]), mode, cval)) {
+            Dense2dGeom D;
+            D.dimx = unsigned(shape[x_axis]);
+            long long xs = 1;
+            for (int a = x_axis + 1; a < 4; ++a) xs *= shape[a];
+            D.xs = unsigned(xs);
+            D.oy = int(origin[s_axis]);
+            D.ox = int(origin[x_axis]);
+            int rc2 = launch_dense2d(dtype, int(kshape[s_axis]), int(kshape[x_axis]), TG, D, in, out, weights, st);
+            if (rc2 <= 0) return rc2;                                   // 0 done, < 0 error, > 0 no instantiation
+        }
+    }
+    if (!taps.empty() && taps.size() <= size_t(MAX_SMEM_TAPS) && is_contiguous(shape, in_strides) &&
+        is_contiguous(shape, out_strides) && s_axis < 3 && make_tile(TG, shape, s_axis, hi[s_axis] - lo[s_axis] + 1, mode, cval)) {
+        TrailGeom R;
+        memset(&R, 0, sizeof(R));
+        R.ntrail = 3 - s_axis;
+        long long str = 1;
+        for (int a = 3; a > s_axis; --a) {
+            const int k = a - s_axis - 1;
+            R.dim[k] = unsigned(shape[a]);
+            R.str[k] = str;
+            R.lo[k] = lo[a];
+            R.hi[k] = hi[a];
+            str *= shape[a];
+        }
+        R.slo = lo[s_axis];
+        R.shi = hi[s_axis];
+        std::vector<TiledTap> tt(taps.size());
+        for (size_t i = 0; i < taps.size(); ++i) {
+            tt[i].w = taps[i].w;
+            tt[i].ds = taps[i].off[s_axis];
+            tt[i].lin = (long long)taps[i].off[s_axis] * TG.inner;
+            for (int k = 0; k < 3; ++k) tt[i].dt[k] = 0;
+            for (int k = 0; k < R.ntrail; ++k) {
+                tt[i].dt[k] = taps[i].off[s_axis + 1 + k];
+                tt[i].lin += (long long)tt[i].dt[k] * R.str[k];
+            }
+        }
+        TiledTap* dtt = nullptr;
+        FLT_CUDA_TRY(cudaMallocAsync((void**)&dtt, tt.size() * sizeof(TiledTap), st));
+        FLT_CUDA_TRY(cudaMemcpyAsync(dtt, tt.data(), tt.size() * sizeof(TiledTap), cudaMemcpyHostToDevice, st));
+        const unsigned grid = unsigned(TG.outer * TG.nbn * TG.nbi);
+        if (dtype == NDFLT_F64)
+            correlate_nd_tiled_kernel<double><<<grid, TILE_THREADS, 0, st>>>(TG, R, (const double*)in, (double*)out, dtt, int(tt.size()));
+        else
+            correlate_nd_tiled_kernel<float><<<grid, TILE_THREADS, 0, st>>>(TG, R, (const float*)in, (float*)out, dtt, int(tt.size()));
+        g_flt_launches++;
+        FLT_CUDA_TRY(cudaGetLastError());
+        FLT_CUDA_TRY(cudaFreeAsync(dtt, st));
+        return NDNLM_OK;
+    }
     Tap* dtaps = nullptr;
     const size_t nb = (taps.empty() ? 1 : taps.size()) * sizeof(Tap);
     FLT_CUDA_TRY(cudaMallocAsync((void**)&dtaps, nb, st));
@@ -281,6 +432,108 @@ extern "C" int ndflt_correlate(const void* in, void* out, const int64_t shape[4]
     FLT_CUDA_TRY(cudaGetLastError());
     FLT_CUDA_TRY(cudaFreeAsync(dtaps, st));
     return NDNLM_OK;
+}
+
+template <typename T, int SYM>
+static void launch_1d_fast(const TileGeom& TG, const void* in, void* out, const double* dw, int size1, int size2, int origin,
+                           cudaStream_t st) {
+    if (TG.inner == 1) {
+        constexpr int U = 4;
+        const long long total = TG.outer * TG.n;
+        const unsigned grid = unsigned((total + TILE_THREADS * U - 1) / (TILE_THREADS * U));
+        correlate_1d_rows_kernel<T, SYM, U><<<grid, TILE_THREADS, 0, st>>>(total, unsigned(TG.n), (const T*)in, (T*)out, dw, size1,
+                                                                          size2, origin, TG.mode, TG.cval);
+    } else {
+        const unsigned grid = unsigned(TG.outer * TG.nbn * TG.nbi);
+        correlate_1d_tiled_kernel<T, SYM><<<grid, TILE_THREADS, 0, st>>>(TG, (const T*)in, (T*)out, dw, size1, size2, origin);
+    }
+}
+
+// Register sliding-window kernels for symmetric / antisymmetric kernels of half-width 1..8 (Gaussian sigma <= 2 with the
+// default truncation, boxcar-like 1-D kernels); U = 32 consecutive rows per thread.
+constexpr int SLIDE_U = 32;
+template <typename T, int SYM, int S1>
+static void launch_slide(const TileGeom& TG, const void* in, void* out, const double* dw, int origin, cudaStream_t st) {
+    TileGeom G = TG;
+    G.U = SLIDE_U;
+    G.nbn = unsigned((G.n + (long long)G.RP * SLIDE_U - 1) / ((long long)G.RP * SLIDE_U));
+    const unsigned grid = unsigned(G.outer * G.nbn * G.nbi);
+    correlate_1d_slide_kernel<T, SYM, S1, SLIDE_U><<<grid, TILE_THREADS, 0, st>>>(G, (const T*)in, (T*)out, dw, origin);
+}
+template <typename T, int SYM>
+static bool try_slide(const TileGeom& TG, const void* in, void* out, const double* dw, int size1, int size2, int origin,
+                      cudaStream_t st) {
+    if (TG.inner == 1 || size1 != size2 || size1 < 1 || size1 > 8) return false;
+    if (TG.outer * ((TG.n + (long long)TG.RP * SLIDE_U - 1) / ((long long)TG.RP * SLIDE_U)) * TG.nbi > 0x7fffffffLL) return false;
+    switch (size1) {
+        case 1: launch_slide<T, SYM, 1>(TG, in, out, dw, origin, st); break;
+        case 2: launch_slide<T, SYM, 2>(TG, in, out, dw, origin, st); break;
+        case 3: launch_slide<T, SYM, 3>(TG, in, out, dw, origin, st); break;
+        case 4: launch_slide<T, SYM, 4>(TG, in, out, dw, origin, st); break;
+        case 5: launch_slide<T, SYM, 5>(TG, in, out, dw, origin, st); break;
+        case 6: launch_slide<T, SYM, 6>(TG, in, out, dw, origin, st); break;
+        case 7: launch_slide<T, SYM, 7>(TG, in, out, dw, origin, st); break;
+        default: launch_slide<T, SYM, 8>(TG, in, out, dw, origin, st); break;
+    }
+    return true;
+}
+
+// Fastest-axis passes through shared memory (kernels up to 129 taps).
+template <typename T, int SYM, int S1>
+static void launch_rows_smem(const RowsGeom& RG, size_t smem, const void* in, void* out, const double* dw, int size1, int size2,
+                             int origin, cudaStream_t st) {
+    const unsigned grid = unsigned(((RG.lines + RG.LN - 1) / RG.LN) * RG.nbc);
+    correlate_1d_rows_smem_kernel<T, SYM, S1><<<grid, TILE_THREADS, smem, st>>>(RG, (const T*)in, (T*)out, dw, size1, size2, origin);
+}
+template <typename T, int SYM>
+static bool try_rows_smem(const TileGeom& TG, const void* in, void* out, const double* dw, int size1, int size2, int origin,
+                          cudaStream_t st) {
+    const int nw = size1 + size2 + 1;
+    if (TG.inner != 1 || nw > 129 || TG.n > 0x7fffffffLL) return false;
+    RowsGeom RG;
+    RG.lines = TG.outer;
+    RG.n = unsigned(TG.n);
+    RG.CW = int(TG.n < 256 ? TG.n : 256);
+    RG.pitch = RG.CW + nw - 1;
+    int ln = 2048 / RG.CW;                                           // ~8 outputs per thread
+    const int cap = int((40960 - 8 * nw) / (8 * RG.pitch));          // <= 40 KB of shared memory
+    ln = ln < cap ? ln : cap;
+    if (ln < 1) return false;
+    if ((long long)ln > RG.lines) ln = int(RG.lines);
+    RG.LN = ln;
+    RG.nbc = unsigned((TG.n + RG.CW - 1) / RG.CW);
+    if (((RG.lines + RG.LN - 1) / RG.LN) * RG.nbc > 0x7fffffffLL) return false;
+    RG.mode = TG.mode;
+    RG.cval = TG.cval;
+    const size_t smem = size_t(RG.LN) * RG.pitch * 8 + size_t(nw) * 8;
+    if (SYM != 0 && size1 == size2 && size1 >= 1 && size1 <= 8) {
+        switch (size1) {
+            case 1: launch_rows_smem<T, SYM, 1>(RG, smem, in, out, dw, size1, size2, origin, st); break;
+            case 2: launch_rows_smem<T, SYM, 2>(RG, smem, in, out, dw, size1, size2, origin, st); break;
+            case 3: launch_rows_smem<T, SYM, 3>(RG, smem, in, out, dw, size1, size2, origin, st); break;
+            case 4: launch_rows_smem<T, SYM, 4>(RG, smem, in, out, dw, size1, size2, origin, st); break;
+            case 5: launch_rows_smem<T, SYM, 5>(RG, smem, in, out, dw, size1, size2, origin, st); break;
+            case 6: launch_rows_smem<T, SYM, 6>(RG, smem, in, out, dw, size1, size2, origin, st); break;
+            case 7: launch_rows_smem<T, SYM, 7>(RG, smem, in, out, dw, size1, size2, origin, st); break;
+            default: launch_rows_smem<T, SYM, 8>(RG, smem, in, out, dw, size1, size2, origin, st); break;
+        }
+    } else {
+        launch_rows_smem<T, SYM, 0>(RG, smem, in, out, dw, size1, size2, origin, st);
+    }
+    return true;
+}
+
+template <typename T>
+static void launch_1d_fast_sym(int sym, const TileGeom& TG, const void* in, void* out, const double* dw, int size1, int size2,
+                               int origin, cudaStream_t st) {
+    if (sym > 0 && try_slide<T, 1>(TG, in, out, dw, size1, size2, origin, st)) return;
+    if (sym < 0 && try_slide<T, -1>(TG, in, out, dw, size1, size2, origin, st)) return;
+    if (sym > 0 && try_rows_smem<T, 1>(TG, in, out, dw, size1, size2, origin, st)) return;
+    if (sym < 0 && try_rows_smem<T, -1>(TG, in, out, dw, size1, size2, origin, st)) return;
+    if (sym == 0 && try_rows_smem<T, 0>(TG, in, out, dw, size1, size2, origin, st)) return;
+    if (sym > 0) launch_1d_fast<T, 1>(TG, in, out, dw, size1, size2, origin, st);
+    else if (sym < 0) launch_1d_fast<T, -1>(TG, in, out, dw, size1, size2, origin, st);
+    else launch_1d_fast<T, 0>(TG, in, out, dw, size1, size2, origin, st);
 }
 
 template <typename T>
@@ -326,8 +579,18 @@ extern "C" int ndflt_correlate1d(const void* in, void* out, const int64_t shape[
     double* dw = nullptr;
     FLT_CUDA_TRY(cudaMallocAsync((void**)&dw, size_t(nweights) * sizeof(double), st));
     FLT_CUDA_TRY(cudaMemcpyAsync(dw, weights, size_t(nweights) * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (dtype == NDFLT_F64) launch_1d<double>(sym, G, in, out, dw, axis, size1, size2, int(origin), st);
-    else launch_1d<float>(sym, G, in, out, dw, axis, size1, size2, int(origin), st);
+    TileGeom TG;
+    const bool fast = nweights <= MAX_SMEM_WEIGHTS && is_contiguous(shape, in_strides) && is_contiguous(shape, out_strides) &&
+                      shape[axis] <= 0xffffffffLL && make_tile(TG, shape, axis, int(nweights), mode, cval) &&
+                      (TG.inner > 1 || (TG.outer * TG.n + TILE_THREADS * 4 - 1) / (TILE_THREADS * 4) <= 0x7fffffffLL);
+    if (fast) {
+        if (dtype == NDFLT_F64) launch_1d_fast_sym<double>(sym, TG, in, out, dw, size1, size2, int(origin), st);
+        else launch_1d_fast_sym<float>(sym, TG, in, out, dw, size1, size2, int(origin), st);
+    } else if (dtype == NDFLT_F64) {
+        launch_1d<double>(sym, G, in, out, dw, axis, size1, size2, int(origin), st);
+    } else {
+        launch_1d<float>(sym, G, in, out, dw, axis, size1, size2, int(origin), st);
+    }
     g_flt_launches++;
     FLT_CUDA_TRY(cudaGetLastError());
     FLT_CUDA_TRY(cudaFreeAsync(dw, st));

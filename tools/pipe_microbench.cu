@@ -132,6 +132,48 @@ __global__ void k_shfl(float* out, float a, float b, long long* cyc) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
+__global__ void k_dadd(float* out, float a, float b, long long* cyc) {
+  double r[UNROLL]; const double x = a;
+#pragma unroll
+  for (int i = 0; i < UNROLL; i++) r[i] = threadIdx.x * 0.001 + i;
+  long long t0 = clock64();
+  for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < UNROLL; i++) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(r[i]) : "d"(x));
+  }
+  long long t1 = clock64();
+  double s = 0; for (int i = 0; i < UNROLL; i++) s += r[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+__global__ void k_dfma(float* out, float a, float b, long long* cyc) {
+  double r[UNROLL]; const double x = a, y = b;
+#pragma unroll
+  for (int i = 0; i < UNROLL; i++) r[i] = threadIdx.x * 0.001 + i;
+  long long t0 = clock64();
+  for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < UNROLL; i++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(r[i]) : "d"(x), "d"(y));
+  }
+  long long t1 = clock64();
+  double s = 0; for (int i = 0; i < UNROLL; i++) s += r[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+__global__ void k_f2d(float* out, float a, float b, long long* cyc) {
+  float r[UNROLL];
+#pragma unroll
+  for (int i = 0; i < UNROLL; i++) r[i] = threadIdx.x * 0.001f + i;
+  long long t0 = clock64();
+  for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < UNROLL; i++) { double d; asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(r[i])); asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(r[i]) : "d"(d)); }
+  }
+  long long t1 = clock64();
+  float s = 0; for (int i = 0; i < UNROLL; i++) s += r[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
 template <int VEC>
 __global__ void k_lds(float* out, float a, float b, long long* cyc) {
   extern __shared__ float4 sm[];
@@ -216,11 +258,14 @@ int main() {
     {"FMNMX", k_fmnmx, UNROLL, 1, 0},
     {"MUFU.EX2", k_ex2, UNROLL, 1, 0},
     {"SHFL.UP", k_shfl, UNROLL, 1, 0},
+    {"DADD", k_dadd, UNROLL, 1, 0},
+    {"DFMA", k_dfma, UNROLL, 1, 0},
+    {"F2F f32->f64->f32 (2 instr)", k_f2d, 2 * UNROLL, 1, 0},
     {"LDS.128", k_lds<4>, UNROLL, 1, 65536},
     {"LDS.32", k_lds<1>, UNROLL, 1, 65536},
     {"NLM-mix (22 instr / pair-step)", k_mix, 4 * 22, 1, 0},
   };
-  for (int threads : {256, 512, 1024}) {
+  for (int threads : {1024}) {
     for (auto& t : tests) {
       int blocks = sms * (t.smem ? 1 : (1024 / threads));
       if (t.smem && threads != 1024) continue;
