@@ -26,6 +26,11 @@
 #ifndef NDNLM_KEEP_OWN
 #define NDNLM_KEEP_OWN 0   // 1: keep my own exchanged sums in registers instead of re-reading them from shared memory
 #endif
+#ifndef NDNLM_DEBUG_CTA_SYNC
+#define NDNLM_DEBUG_CTA_SYNC 0   // 1: replace the neighbour-only mbarrier protocol of the W exchange by two CTA barriers per
+                                 //    chunk (slow; lets compute-sanitizer's racecheck, which does not model remote mbarrier
+                                 //    arrivals, verify the data flow itself)
+#endif
 #ifndef NDNLM_FOLD_T
 #define NDNLM_FOLD_T double   // type of the second-level weight-sum accumulators
 #endif
@@ -350,7 +355,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         constexpr int NJ = decltype(nj_tag)::value;
         constexpr bool CENTRE = decltype(centre_tag)::value;
         constexpr int WNJ = E + NJ - 1;
-        if constexpr (CENTRE && FW > 0) mbar_wait(mbar_empty + wid, xpar ^ 1);
+        if constexpr (CENTRE && FW > 0 && !NDNLM_DEBUG_CTA_SYNC) mbar_wait(mbar_empty + wid, xpar ^ 1);
         [[maybe_unused]] float2 own[NDNLM_KEEP_OWN != 0 ? NJ : 1][L / 2];
 
         float4 n[NV4][WNJ];
@@ -414,7 +419,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
             } else {
                 // before the first store of this chunk: my readers must be done with the previous round
                 // (on a fresh barrier the wait for the "previous" parity returns at once)
-                if constexpr (!CENTRE) {
+                if constexpr (!CENTRE && !NDNLM_DEBUG_CTA_SYNC) {
                     if (j == 0) mbar_wait(mbar_empty + wid, xpar ^ 1);
                 }
                 if constexpr (L == 4) {
@@ -434,13 +439,14 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         // ---- phase B: box sum along W through shared memory, then weights ----
         if constexpr (FW > 0) {
             __syncwarp();
+            if constexpr (NDNLM_DEBUG_CTA_SYNC) __syncthreads();
             // release: my sums are published -- tell every valid row that reads them (lanes 0..2FW-1, one each)
-            if (lane < 2 * FW) {
+            if (!NDNLM_DEBUG_CTA_SYNC && lane < 2 * FW) {
                 const int d = (lane < FW) ? lane - FW : lane - FW + 1;
                 if (wid + d >= FW && wid + d < NWARPS - FW) mbar_arrive(mbar_full + wid + d);
             }
             if (wvalid) {
-                mbar_wait(mbar_full + wid, xpar);                  // acquire: all rows I read are published
+                if constexpr (!NDNLM_DEBUG_CTA_SYNC) mbar_wait(mbar_full + wid, xpar);   // acquire: all rows I read are published
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     if constexpr (CENTRE) {
@@ -477,11 +483,12 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                     weigh(D, j);
                 }
                 __syncwarp();
-                if (lane < 2 * FW) {                                  // done reading the neighbour rows
+                if (!NDNLM_DEBUG_CTA_SYNC && lane < 2 * FW) {         // done reading the neighbour rows
                     const int d = (lane < FW) ? lane - FW : lane - FW + 1;
                     mbar_arrive(mbar_empty + wid + d);
                 }
             }
+            if constexpr (NDNLM_DEBUG_CTA_SYNC) __syncthreads();
             xpar ^= 1;
         }
     };

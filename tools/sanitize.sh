@@ -1,0 +1,19 @@
+#!/bin/bash
+# compute-sanitizer sweep (GPU box): memcheck + racecheck + synccheck on small plans of every kernel family.
+mkdir -p gpurun_out
+OUT=gpurun_out/sanitizer.txt
+: > $OUT
+run() {  # tool, label, command...
+  tool=$1; label=$2; shift 2
+  echo "== $tool : $label" >> $OUT
+  timeout 600 compute-sanitizer --tool $tool --print-limit 5 "$@" 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error|error|hazard|RESULT|passed|failed" | head -12 >> $OUT
+}
+for tool in memcheck racecheck synccheck; do
+  run $tool "nlm tiled f=1 cfg3-like (TMA, 2 passes)" python tools/dev_parity.py --case 2
+  run $tool "nlm tiled 2-D f=1"                       python tools/dev_parity.py --case 4
+  run $tool "nlm tiled n_eff"                         python tools/dev_parity.py --case 11
+  run $tool "nlm tiled f=2"                           python tools/dev_parity.py --case 12
+done
+run memcheck "sibling filters (all kernels)" python -m pytest tests/test_sibling_filters.py -q -m gpu -x
+run memcheck "nlm gpu parity subset" python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "matches_oracle_float32 or sharded or slab"
+cat $OUT
