@@ -52,7 +52,8 @@ extern "C" {
 /* ---- kernel selection ---- */
 #define NDNLM_KERNEL_AUTO     0  /* tiled fp32 kernel when the configuration has an instantiation, else generic */
 #define NDNLM_KERNEL_GENERIC  1  /* reference-faithful one-thread-per-voxel kernel (fp64 weights), any r/f/V      */
-#define NDNLM_KERNEL_TILED    2  /* TMA-tiled fp32 kernel; error if not instantiated for this configuration      */
+#define NDNLM_KERNEL_TILED    2  /* TMA-tiled fp32 kernel; error if not instantiated for this configuration.      */
+                                 /* With float64 data: staged as float32, result widened back (opt-in fp32 compute) */
 
 /* ---- how the two ends of user axis `shard_axis` are padded by ndnlm_stage ---- */
 #define NDNLM_EDGE_REFLECT 0     /* global edge: reflect locally (reference `_idx`, nd/_filters.pyx:34-40) */

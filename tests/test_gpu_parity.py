@@ -112,6 +112,19 @@ def test_float64_matches_oracle(dev, c_oracle, shape, r, f):
         assert out.dtype == np.float64 and scaled_err(out, ref) < TOL64, (plan.kernel_name, sem)
 
 
+@pytest.mark.parametrize("shape,r,f", [CASES[1], CASES[4], CASES[10]])
+def test_float64_data_on_the_fp32_tiled_kernel_on_request(dev, c_oracle, shape, r, f):
+    """kernel='tiled' with float64 data: staged as float32, result widened back -- north_star's fp32 compute, far
+    inside its 1e-4 (the default for float64 data stays the float64 generic kernel, see above)."""
+    a = sar_like(shape, seed=5, dtype=np.float64)
+    ref = c_oracle.nlmeans(a, r, f, 0.3, 0.6)
+    out, plan = run_plan(dev, a, r, f, 0.3, 0.6, kernel="tiled")
+    assert plan.is_tiled and out.dtype == np.float64
+    assert scaled_err(out, ref) < 5e-6, plan.kernel_name
+    out32, _ = run_plan(dev, a.astype(np.float32), r, f, 0.3, 0.6, kernel="tiled")
+    assert np.array_equal(out.astype(np.float32), out32)          # exactly the float32 path
+
+
 @pytest.mark.parametrize("shape,r,f", [CASES[0], CASES[4], CASES[10]])
 def test_reference_compiled_semantics(dev, c_oracle, shape, r, f):
     a = sar_like(shape, seed=4, dtype=np.float32)

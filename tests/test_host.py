@@ -71,8 +71,11 @@ def test_plan_kernel_selection():
     assert device.Plan((40, 50, 30, 4), (2, 2, 1), (0, 0, 0), 1, 1, semantics="reference_compiled").is_tiled
     assert device.Plan((1, 206, 500, 4), (0, 3, 3), (0, 1, 1), 1, 1).is_tiled
     assert not device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, kernel="generic").is_tiled
-    with pytest.raises(ValueError):
-        device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64, kernel="tiled")
+    # float64 data: generic float64 kernel by default, the fp32 tiled kernel only on explicit request
+    p64 = device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64, kernel="tiled")
+    assert p64.is_tiled and p64.padded_bytes == (40 + 6) * (50 + 6) * (30 + 4) * 16
+    with pytest.raises(ValueError):                                  # V > 8 has no tiled instantiation
+        device.Plan((40, 50, 30, 9), (2, 2, 1), (1, 1, 1), 1, 1, kernel="tiled")
 
 
 def test_plan_errors_map_to_reference_exceptions():
