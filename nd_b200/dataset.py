@@ -120,6 +120,44 @@ class Dataset:
         return True
 
 
+def save_dataset(ds, path):
+    """Write `ds` to ONE file (NumPy .npz: variables, coords, and a JSON header with dims / attrs).
+    Stand-in for the reference's `to_netcdf` (nd/io.py): NetCDF libraries are absent in this image."""
+    import json
+    meta = {'vars': {k: list(v.dims) for k, v in ds.data_vars.items()}, 'coords': list(ds.coords),
+            'attrs': {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in ds.attrs.items()}}
+    arrays = {'v__' + k: v.values for k, v in ds.data_vars.items()}
+    arrays.update({'c__' + k: c for k, c in ds.coords.items()})
+    with open(path, 'wb') as f:
+        np.savez(f, __meta__=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
+
+
+def open_dataset(path):
+    """Inverse of `save_dataset` (stand-in for the reference's `open_netcdf`)."""
+    import json
+    with np.load(path, allow_pickle=False) as z:
+        meta = json.loads(bytes(z['__meta__']).decode())
+        ds = Dataset(coords=OrderedDict((k, z['c__' + k]) for k in meta['coords']), attrs=meta['attrs'])
+        for k, dims in meta['vars'].items():
+            ds[k] = (tuple(dims), z['v__' + k])
+    return ds
+
+
+def concat(datasets, dim):
+    """Concatenate datasets along `dim` (variables and the coordinate of that dimension)."""
+    first = datasets[0]
+    coords = OrderedDict(first.coords)
+    if dim in coords:
+        coords[dim] = np.concatenate([d.coords[dim] for d in datasets])
+    out = Dataset(coords=coords, attrs=first.attrs)
+    for k, v in first.data_vars.items():
+        if dim in v.dims:
+            out[k] = (v.dims, np.concatenate([d[k].values for d in datasets], axis=v.dims.index(dim)))
+        else:
+            out[k] = (v.dims, v.values)
+    return out
+
+
 def generate_test_dataset(dims=None, var=('C11', 'C12__im', 'C12__re', 'C22'), mean=0, sigma=1,
                           random_seed=42, dtype=np.float64):
     """NumPy-only restatement of the reference fixture generator (nd/testing.py:34-70):
