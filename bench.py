@@ -228,6 +228,26 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_cpus(gpu_index):
+    """One process per GPU: run on the CPUs that are local to this rank's GPU (NVML's affinity mask), so that the
+    pinned host chunk of the e2e leg is allocated on the NUMA node its PCIe link hangs off.  Returns the CPU count
+    or None when NVML / the affinity call is unavailable (nothing changes then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -244,12 +264,16 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+    # stdout carries exactly ONE JSON line: whatever libraries print on fd 1 meanwhile (NCCL announces its version
+    # there) is sent to stderr, and the line is written to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL announces its version on stdout by default; stdout carries exactly ONE JSON line here
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     wl = args.workload
@@ -356,6 +380,7 @@ def run_ours(args):
         e2e = {"value": world * e2e_rows * nx * nt * e2e_steps / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": ebytes, "d2h_bytes_per_step": ebytes, "rows_per_gpu": e2e_rows,
                "steps": e2e_steps, "api": "nd_b200._filters._pixelwise_nlmeans_3d(host arr, host output, r, f, sigma, h, n_eff)",
+               "cpus_bound_to_gpu": numa,
                "note": "rank-local host chunk incl. r+f buffer rows of its neighbours (the reference's xr_split rule); "
                        "slab-pipelined H2D / kernels / D2H on three streams; only interior rows are counted",
                "checksum": float(np.float64(a_out[lo_buf:lo_buf + e2e_rows:max(1, e2e_rows // 64)].sum()))}
@@ -410,7 +435,8 @@ def run_ours(args):
                        "plan": info},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "no_solution_flag": flag}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
