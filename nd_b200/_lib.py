@@ -28,6 +28,8 @@ SYMBOLS = [
 ]
 # every symbol include/ndflt.h declares (sibling filters)
 FLT_SYMBOLS = ["ndflt_correlate", "ndflt_correlate1d", "ndflt_launch_count", "ndflt_last_error"]
+# every symbol include/ndchg.h declares (omnibus change detection)
+CHG_SYMBOLS = ["ndchg_change_detection", "ndchg_omnibus_probability", "ndchg_last_error"]
 
 
 class Info(ctypes.Structure):
@@ -112,6 +114,12 @@ def lib():
     L.ndflt_launch_count.restype = ctypes.c_int64
     L.ndflt_last_error.argtypes = []
     L.ndflt_last_error.restype = ctypes.c_char_p
+    L.ndchg_change_detection.argtypes = [vp, i64p, i64p, ctypes.c_int, vp, ctypes.c_double, ctypes.c_uint32, vp]
+    L.ndchg_change_detection.restype = ctypes.c_int
+    L.ndchg_omnibus_probability.argtypes = [vp, i64p, i64p, ctypes.c_int, vp, ctypes.c_uint32, vp]
+    L.ndchg_omnibus_probability.restype = ctypes.c_int
+    L.ndchg_last_error.argtypes = []
+    L.ndchg_last_error.restype = ctypes.c_char_p
     _lib = L
     return L
 

@@ -36,6 +36,48 @@ class Variable:
         return Variable(self.dims, self.values.copy() if deep else self.values)
 
 
+class DataArray:
+    """A named array with dims, coords and attrs -- the subset of `xarray.DataArray` the change detectors return
+    (reference nd/change.py:69-75)."""
+
+    def __init__(self, values, dims, coords=None, attrs=None, name=None):
+        self.values = np.asarray(values)
+        self.dims = tuple(dims)
+        if self.values.ndim != len(self.dims):
+            raise ValueError('dims %r do not match data of shape %r' % (self.dims, self.values.shape))
+        self.coords = OrderedDict((k, np.asarray(v)) for k, v in (coords or {}).items())
+        self.attrs = OrderedDict(attrs or {})
+        self.name = name
+
+    @property
+    def shape(self):
+        return self.values.shape
+
+    @property
+    def dtype(self):
+        return self.values.dtype
+
+    def isel(self, **indexers):
+        idx = tuple(indexers.get(d, slice(None)) for d in self.dims)
+        dims = tuple(d for d in self.dims if not isinstance(indexers.get(d, slice(None)), (int, np.integer)))
+        coords = OrderedDict((k, (c[indexers[k]] if k in indexers else c)) for k, c in self.coords.items())
+        return DataArray(self.values[idx], dims, coords, self.attrs, self.name)
+
+    def sum(self, dim=None):
+        if dim is None:
+            return self.values.sum()
+        axis = self.dims.index(dim)
+        return DataArray(self.values.sum(axis=axis), self.dims[:axis] + self.dims[axis + 1:],
+                         OrderedDict((k, c) for k, c in self.coords.items() if k != dim), self.attrs, self.name)
+
+    def all(self):
+        return bool(self.values.all())
+
+    def __eq__(self, other):
+        return DataArray(self.values == (other.values if isinstance(other, DataArray) else other), self.dims,
+                         self.coords, self.attrs, self.name)
+
+
 class Dataset:
     def __init__(self, data_vars=None, coords=None, attrs=None):
         self.data_vars = OrderedDict()
