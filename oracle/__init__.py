@@ -22,4 +22,12 @@ Three oracles, in decreasing order of authority:
 
 Parity status: PINNED -- every oracle is checked against outputs of the unmodified
 reference kernel run in this container (`tests/golden/make_golden.py`).
+
+Oracles of the rows built after the hot path:
+
+4. `oracle.ndimage_numpy`  -- NumPy restatement of the scipy.ndimage arithmetic below the sibling
+                              filters (row N2).  PINNED: bit-exact against scipy itself on the CPU
+                              (`tests/test_sibling_filters.py`); the GPU tests then use scipy directly.
+5. `oracle.omnibus_oracle` -- NumPy restatement of `nd/_change.pyx` (row N4).  PARITY UNPINNED: the
+                              reference needs GSL, which is not installed, so it cannot be run here.
 """

@@ -190,6 +190,24 @@ def test_shard_plan_rejects_shards_smaller_than_halo():
         ShardPlan(16, 8, 6)
 
 
+@pytest.mark.parametrize("n,rows,halo", [(4096, 126, 6), (4108, 126, 6), (100, 48, 4), (200, 64, 0), (130, 64, 6), (50, 100, 3),
+                                         (37, 5, 6)])
+def test_slab_plan_from_rows(n, rows, halo):
+    """Slabs of the host pipeline: contiguous, complete, every slab tall enough to carry its halo, buffers clipped."""
+    sp = ShardPlan.from_rows(n, rows, halo)
+    assert sp.ranges[0][0] == 0 and sp.ranges[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(sp.ranges[:-1], sp.ranges[1:]))
+    if sp.nshards > 1:
+        assert all(hi - lo >= halo + 1 for lo, hi in sp.ranges)
+    for i, (lo, hi) in enumerate(sp.ranges):
+        blo, bhi = sp.buffered_range(i)
+        assert blo == max(lo - halo, 0) and bhi == min(hi + halo, n)
+        if i > 0:
+            assert lo - blo == halo                      # interior edges always have the full halo available
+        if i < sp.nshards - 1:
+            assert bhi - hi == halo
+
+
 def test_dataset_standin_roundtrip():
     ds = generate_test_dataset(dims={'y': 6, 'x': 7, 'time': 3})
     assert list(ds.data_vars) == ['C11', 'C12__im', 'C12__re', 'C22']

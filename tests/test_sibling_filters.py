@@ -110,6 +110,31 @@ def test_compute_path_fails_loudly_without_gpu():
         GaussianFilter(('y', 'x')).apply(generate_test_dataset(dims={'y': 8, 'x': 8, 'time': 2}))
 
 
+# ---- CPU: the restated algorithm is pinned against scipy itself, bit for bit --------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_numpy_restatement_of_ni_filters_equals_scipy(dtype):
+    """oracle/ndimage_numpy.py is the statement of scipy's NI_Correlate / NI_Correlate1D / NI_ExtendLine the CUDA
+    kernels were written from; it must reproduce scipy exactly (summation order, separate multiply and add,
+    boundary extension, origins, kernel flip)."""
+    from oracle import ndimage_numpy as on
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(7, 9, 5)).astype(dtype)
+    k = rng.random((3, 4, 1))
+    k[1, 2, 0] = 0.0
+    for mode in ("reflect", "constant", "nearest", "mirror", "wrap"):
+        for origin in (0, (1, -1, 0)):
+            assert np.array_equal(on.correlate(a, k, mode, 0.7, origin), sn.correlate(a, k, mode=mode, cval=0.7, origin=origin))
+            assert np.array_equal(on.convolve(a, k, mode, 0.7, origin), sn.convolve(a, k, mode=mode, cval=0.7, origin=origin))
+        w_long = rng.random(13)                                       # longer than two of the axes
+        for axis in range(3):
+            for w in (w_long, np.array([1.0, 2.0, 3.0, 2.0, 1.0]), np.array([-1.0, 0.0, 1.0]), np.array([0.2, 0.5, 0.1, 0.9])):
+                for origin in (0, 1, -1):
+                    assert np.array_equal(on.correlate1d(a, w, axis, mode, -0.3, origin),
+                                          sn.correlate1d(a, w, axis=axis, mode=mode, cval=-0.3, origin=origin)), (mode, axis, len(w), origin)
+    for sigma in (1, [1.5, 0, 0.8], 2.0):
+        assert np.array_equal(on.gaussian_filter(a, sigma), sn.gaussian_filter(a, sigma))
+
+
 # ---- GPU: bit-exact parity with scipy ------------------------------------------------------------------
 def _rand(shape, dtype, seed=0):
     return np.random.default_rng(seed).normal(size=shape).astype(dtype)
