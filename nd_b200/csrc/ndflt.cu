@@ -311,6 +311,27 @@ static int launch_dense2d(int dtype, int kh, int kw, const TileGeom& TG, const D
     return 1;
 }
 
+// Dense 3 x 3 x 3 footprints over the tiled axis and two trailing axes.
+template <typename T>
+static int launch_dense3d_t(const TileGeom& TG, const Dense3dGeom& D, const void* in, void* out, const double* weights,
+                            cudaStream_t st) {
+    constexpr int U3 = 8;
+    TileGeom G = TG;
+    G.U = U3;
+    const long long nbn = (G.n + (long long)G.RP * U3 - 1) / ((long long)G.RP * U3);
+    if (G.outer * nbn * G.nbi > 0x7fffffffLL) return 1;
+    G.nbn = unsigned(nbn);
+    double* dw = nullptr;
+    FLT_CUDA_TRY(cudaMallocAsync((void**)&dw, sizeof(double) * 27, st));
+    FLT_CUDA_TRY(cudaMemcpyAsync(dw, weights, sizeof(double) * 27, cudaMemcpyHostToDevice, st));
+    correlate_3d_slide_kernel<T, 3, 3, 3, U3><<<unsigned(G.outer * G.nbn * G.nbi), TILE_THREADS, 0, st>>>(
+        G, D, (const T*)in, (T*)out, dw);
+    g_flt_launches++;
+    FLT_CUDA_TRY(cudaGetLastError());
+    FLT_CUDA_TRY(cudaFreeAsync(dw, st));
+    return NDNLM_OK;
+}
+
 extern "C" int ndflt_correlate(const void* in, void* out, const int64_t shape[4], const int64_t in_strides[4],
                                const int64_t out_strides[4], int dtype, const double* weights, const int64_t kshape[4],
                                const int64_t origin[4], int mode, double cval, void* stream) {
@@ -376,6 +397,23 @@ extern "C" int ndflt_correlate(const void* in, void* out, const int64_t shape[4]
             D.ox = int(origin[x_axis]);
             int rc2 = launch_dense2d(dtype, int(kshape[s_axis]), int(kshape[x_axis]), TG, D, in, out, weights, st);
             if (rc2 <= 0) return rc2;                                   // 0 done, < 0 error, > 0 no instantiation
+        }
+        // dense 3 x 3 x 3 over the tiled axis and TWO trailing axes
+        int ax3[3], n3 = 0;
+        for (int a = 0; a < 4; ++a)
+            if (kshape[a] > 1 && n3 < 3) ax3[n3++] = a;
+        if (dense && nk == 3 && kshape[ax3[0]] == 3 && kshape[ax3[1]] == 3 && kshape[ax3[2]] == 3 &&
+            is_contiguous(shape, in_strides) && is_contiguous(shape, out_strides) && make_tile(TG, shape, ax3[0], 3, mode, cval)) {
+            Dense3dGeom D;
+            long long xs = 1, ts = 1;
+            for (int a = ax3[1] + 1; a < 4; ++a) xs *= shape[a];
+            for (int a = ax3[2] + 1; a < 4; ++a) ts *= shape[a];
+            D.dimx = unsigned(shape[ax3[1]]); D.xs = unsigned(xs);
+            D.dimt = unsigned(shape[ax3[2]]); D.ts = unsigned(ts);
+            D.oy = int(origin[ax3[0]]); D.ox = int(origin[ax3[1]]); D.ot = int(origin[ax3[2]]);
+            int rc3 = dtype == NDFLT_F64 ? launch_dense3d_t<double>(TG, D, in, out, weights, st)
+                                         : launch_dense3d_t<float>(TG, D, in, out, weights, st);
+            if (rc3 <= 0) return rc3;
         }
     }
     if (!taps.empty() && taps.size() <= size_t(MAX_SMEM_TAPS) && is_contiguous(shape, in_strides) &&

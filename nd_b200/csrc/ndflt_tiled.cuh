@@ -388,6 +388,78 @@ correlate_2d_slide_kernel(const TileGeom G, const Dense2dGeom D, const T* __rest
     else run(std::false_type{});
 }
 
+// ---- dense KH x KW x KT footprints (e.g. BoxcarFilter(dims=('y','x','time'), w=3)) --------------------------------
+// Like correlate_2d_slide_kernel with a second trailing axis.  The boundary extension along the two trailing axes is
+// turned into DATA once per thread (element offsets of the KW x KT columns, -1 = constant), so warps whose lanes sit
+// on the edge of a short fastest axis (a 32-long time axis puts edge lanes into every warp) do not diverge; the
+// extension along the walked axis is warp-uniform.
+struct Dense3dGeom {
+    unsigned dimx, xs;     // first trailing kernel axis: extent, element stride inside the row
+    unsigned dimt, ts;     // second trailing kernel axis (faster than the first)
+    int oy, ox, ot;        // scipy origins
+};
+
+template <typename T, int KH, int KW, int KT, int U>
+__global__ void __launch_bounds__(TILE_THREADS)
+correlate_3d_slide_kernel(const TileGeom G, const Dense3dGeom D, const T* __restrict__ in, T* __restrict__ out,
+                          const double* __restrict__ wbuf) {
+    constexpr int NC = KW * KT;
+    __shared__ double ws[KH * NC];
+    for (int k = threadIdx.x; k < KH * NC; k += TILE_THREADS) ws[k] = wbuf[k];
+    __syncthreads();
+    unsigned b = blockIdx.x;
+    const unsigned bi = b % G.nbi;
+    b /= G.nbi;
+    const unsigned bn = b % G.nbn;
+    const long long o = b / G.nbn;
+    const int tr = int(threadIdx.x) / G.TI, ti = int(threadIdx.x) - tr * G.TI;
+    const long long i = (long long)bi * G.TI + ti;
+    if (tr >= G.RP || i >= G.inner) return;
+    const long long n = G.n, inner = G.inner;
+    const long long row0 = ((long long)bn * G.RP + tr) * U;
+    if (row0 >= n) return;
+    const int ix = int((unsigned(i) / D.xs) % D.dimx), it = int((unsigned(i) / D.ts) % D.dimt);
+    const long long irest = i - (long long)ix * D.xs - (long long)it * D.ts;
+    const T* __restrict__ plane = in + o * n * inner;
+    T* __restrict__ oline = out + o * n * inner + i;
+    long long coff[NC];                                             // element offsets of my KW x KT columns, -1: constant
+#pragma unroll
+    for (int c = 0; c < KW; ++c) {
+        const long long qx = extend_index(ix - (KW / 2) - D.ox + c, D.dimx, G.mode);
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            const long long qt = extend_index(it - (KT / 2) - D.ot + d, D.dimt, G.mode);
+            coff[c * KT + d] = (qx < 0 || qt < 0) ? -1 : irest + qx * D.xs + qt * D.ts;
+        }
+    }
+    auto load_row = [&](const long long pos, double (&dst)[NC]) {
+        const long long q = extend_index(pos, n, G.mode);           // warp-uniform
+        const T* r = plane + (q < 0 ? 0 : q) * inner;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double v = double(__ldg(r + (coff[c] < 0 ? 0 : coff[c])));
+            dst[c] = (q < 0 || coff[c] < 0) ? G.cval : v;
+        }
+    };
+    const long long base = row0 - (KH / 2) - D.oy;
+    double win[KH][NC];
+#pragma unroll
+    for (int r = 0; r < KH - 1; ++r) load_row(base + r, win[r]);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+        const long long row = row0 + k;
+        if (row < n) {
+            load_row(base + k + KH - 1, win[(k + KH - 1) % KH]);
+            double tmp = 0.0;
+#pragma unroll
+            for (int r = 0; r < KH; ++r)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) tmp = __dadd_rn(tmp, __dmul_rn(win[(k + r) % KH][c], ws[r * NC + c]));
+            oline[row * inner] = T(tmp);
+        }
+    }
+}
+
 // ---- N-D correlation (NI_Correlate), tiled around the slowest filtered axis ---------------------------------
 struct TiledTap {
     long long lin;         // element offset of the tap: ds * inner + offset inside the row

@@ -162,6 +162,14 @@ def test_boundary_modes_and_origins_equal_scipy(mode):
                               sn.convolve(a, k, mode=mode, cval=1.5, origin=origin)), (mode, origin)
         assert np.array_equal(_ndimage.correlate(a, k, mode=mode, cval=-2.0, origin=origin),
                               sn.correlate(a, k, mode=mode, cval=-2.0, origin=origin)), (mode, origin)
+    b = _rand((9, 7, 5), np.float32, seed=4)                          # dense 3x3 / 3x3x3 register-window kernels, short axes
+    k3 = np.random.default_rng(6).random((3, 3, 3))
+    for origin in (0, (1, -1, 1), (-1, 0, -1)):
+        assert np.array_equal(_ndimage.correlate(b, k3, mode=mode, cval=0.5, origin=origin),
+                              sn.correlate(b, k3, mode=mode, cval=0.5, origin=origin)), (mode, origin)
+        o2 = origin if origin == 0 else (origin[0], origin[1], 0)
+        assert np.array_equal(_ndimage.convolve(b, k3[:, :, :1], mode=mode, cval=0.5, origin=o2),
+                              sn.convolve(b, k3[:, :, :1], mode=mode, cval=0.5, origin=o2)), (mode, o2)
     w = np.random.default_rng(5).random(15)                           # kernel longer than the axis: repeated extension
     for axis in (0, 1):
         for origin in (0, 3, -7):
