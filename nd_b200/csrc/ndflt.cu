@@ -53,6 +53,17 @@ struct FltDeviceGuard {
     }
 };
 
+// Stream-ordered scratch buffer that is released on every exit path (including failed launches).
+struct AsyncBuf {
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit AsyncBuf(cudaStream_t s) : st(s) {}
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+    ~AsyncBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+};
+
 namespace ndflt {
 
 // NI_ExtendLine (scipy ni_support.c): index of the element that position i (outside [0, n)) stands for;
@@ -286,14 +297,14 @@ static int launch_dense2d_t(const TileGeom& TG, const Dense2dGeom& D, const void
     const long long nbn = (G.n + (long long)G.RP * DENSE_U - 1) / ((long long)G.RP * DENSE_U);
     if (G.outer * nbn * G.nbi > 0x7fffffffLL) return 1;
     G.nbn = unsigned(nbn);
-    double* dw = nullptr;
-    FLT_CUDA_TRY(cudaMallocAsync((void**)&dw, sizeof(double) * KH * KW, st));
+    AsyncBuf wbuf(st);
+    FLT_CUDA_TRY(wbuf.alloc(sizeof(double) * KH * KW));
+    double* dw = (double*)wbuf.p;
     FLT_CUDA_TRY(cudaMemcpyAsync(dw, weights, sizeof(double) * KH * KW, cudaMemcpyHostToDevice, st));
     correlate_2d_slide_kernel<T, KH, KW, DENSE_U><<<unsigned(G.outer * G.nbn * G.nbi), TILE_THREADS, 0, st>>>(
         G, D, (const T*)in, (T*)out, dw);
     g_flt_launches++;
     FLT_CUDA_TRY(cudaGetLastError());
-    FLT_CUDA_TRY(cudaFreeAsync(dw, st));
     return NDNLM_OK;
 }
 static int launch_dense2d(int dtype, int kh, int kw, const TileGeom& TG, const Dense2dGeom& D, const void* in, void* out,
@@ -321,14 +332,14 @@ static int launch_dense3d_t(const TileGeom& TG, const Dense3dGeom& D, const void
     const long long nbn = (G.n + (long long)G.RP * U3 - 1) / ((long long)G.RP * U3);
     if (G.outer * nbn * G.nbi > 0x7fffffffLL) return 1;
     G.nbn = unsigned(nbn);
-    double* dw = nullptr;
-    FLT_CUDA_TRY(cudaMallocAsync((void**)&dw, sizeof(double) * 27, st));
+    AsyncBuf wbuf(st);
+    FLT_CUDA_TRY(wbuf.alloc(sizeof(double) * 27));
+    double* dw = (double*)wbuf.p;
     FLT_CUDA_TRY(cudaMemcpyAsync(dw, weights, sizeof(double) * 27, cudaMemcpyHostToDevice, st));
     correlate_3d_slide_kernel<T, 3, 3, 3, U3><<<unsigned(G.outer * G.nbn * G.nbi), TILE_THREADS, 0, st>>>(
         G, D, (const T*)in, (T*)out, dw);
     g_flt_launches++;
     FLT_CUDA_TRY(cudaGetLastError());
-    FLT_CUDA_TRY(cudaFreeAsync(dw, st));
     return NDNLM_OK;
 }
 
@@ -443,8 +454,9 @@ extern "C" int ndflt_correlate(const void* in, void* out, const int64_t shape[4]
                 tt[i].lin += (long long)tt[i].dt[k] * R.str[k];
             }
         }
-        TiledTap* dtt = nullptr;
-        FLT_CUDA_TRY(cudaMallocAsync((void**)&dtt, tt.size() * sizeof(TiledTap), st));
+        AsyncBuf tbuf(st);
+        FLT_CUDA_TRY(tbuf.alloc(tt.size() * sizeof(TiledTap)));
+        TiledTap* dtt = (TiledTap*)tbuf.p;
         FLT_CUDA_TRY(cudaMemcpyAsync(dtt, tt.data(), tt.size() * sizeof(TiledTap), cudaMemcpyHostToDevice, st));
         const unsigned grid = unsigned(TG.outer * TG.nbn * TG.nbi);
         if (dtype == NDFLT_F64)
@@ -453,12 +465,11 @@ extern "C" int ndflt_correlate(const void* in, void* out, const int64_t shape[4]
             correlate_nd_tiled_kernel<float><<<grid, TILE_THREADS, 0, st>>>(TG, R, (const float*)in, (float*)out, dtt, int(tt.size()));
         g_flt_launches++;
         FLT_CUDA_TRY(cudaGetLastError());
-        FLT_CUDA_TRY(cudaFreeAsync(dtt, st));
         return NDNLM_OK;
     }
-    Tap* dtaps = nullptr;
-    const size_t nb = (taps.empty() ? 1 : taps.size()) * sizeof(Tap);
-    FLT_CUDA_TRY(cudaMallocAsync((void**)&dtaps, nb, st));
+    AsyncBuf gbuf(st);
+    FLT_CUDA_TRY(gbuf.alloc(taps.size() * sizeof(Tap)));
+    Tap* dtaps = (Tap*)gbuf.p;
     if (!taps.empty()) FLT_CUDA_TRY(cudaMemcpyAsync(dtaps, taps.data(), taps.size() * sizeof(Tap), cudaMemcpyHostToDevice, st));
     // (pageable source: cudaMemcpyAsync returns once the host buffer has been staged, so `taps` may go out of scope)
     const int4 omin = make_int4(lo[0], lo[1], lo[2], lo[3]), omax = make_int4(hi[0], hi[1], hi[2], hi[3]);
@@ -468,7 +479,6 @@ extern "C" int ndflt_correlate(const void* in, void* out, const int64_t shape[4]
         correlate_nd_kernel<float><<<flt_blocks(G.total), 256, 0, st>>>(G, (const float*)in, (float*)out, dtaps, int(taps.size()), omin, omax);
     g_flt_launches++;
     FLT_CUDA_TRY(cudaGetLastError());
-    FLT_CUDA_TRY(cudaFreeAsync(dtaps, st));
     return NDNLM_OK;
 }
 
@@ -614,8 +624,9 @@ extern "C" int ndflt_correlate1d(const void* in, void* out, const int64_t shape[
         }
     }
     cudaStream_t st = (cudaStream_t)stream;
-    double* dw = nullptr;
-    FLT_CUDA_TRY(cudaMallocAsync((void**)&dw, size_t(nweights) * sizeof(double), st));
+    AsyncBuf wbuf(st);
+    FLT_CUDA_TRY(wbuf.alloc(size_t(nweights) * sizeof(double)));
+    double* dw = (double*)wbuf.p;
     FLT_CUDA_TRY(cudaMemcpyAsync(dw, weights, size_t(nweights) * sizeof(double), cudaMemcpyHostToDevice, st));
     TileGeom TG;
     const bool fast = nweights <= MAX_SMEM_WEIGHTS && is_contiguous(shape, in_strides) && is_contiguous(shape, out_strides) &&
@@ -631,7 +642,6 @@ extern "C" int ndflt_correlate1d(const void* in, void* out, const int64_t shape[
     }
     g_flt_launches++;
     FLT_CUDA_TRY(cudaGetLastError());
-    FLT_CUDA_TRY(cudaFreeAsync(dw, st));
     return NDNLM_OK;
 }
 
