@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""Development timing (GPU) of the generic one-thread-per-voxel kernel (float64 data / float32 data forced generic)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from nd_b200 import device
+for dtype, kernel in ((np.float64, "auto"), (np.float32, "generic"), (np.float64, "tiled")):
+    shape = (48, 1024, 32, 4)
+    cube = device.synth_cube(*shape).to(torch.float64 if dtype == np.float64 else torch.float32)
+    plan = device.Plan(shape, (5, 5, 2), (1, 1, 1), 0.25, 0.5, -1, dtype=dtype, kernel=kernel)
+    padded = plan.new_padded("cuda"); internal = plan.new_internal_out("cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    plan.stage(cube, padded)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e30
+    for it in range(3):
+        e0.record(); plan.run(padded, internal, flag); e1.record(); torch.cuda.synchronize()
+        if it: best = min(best, e0.elapsed_time(e1))
+    vox = shape[0] * shape[1] * shape[2]
+    print("%-8s %-70s %9.3f ms  %8.1f Mvoxel/s" % (np.dtype(dtype).name, plan.kernel_name, best, vox / best / 1e3), flush=True)
