@@ -43,9 +43,17 @@ class Plan:
         L = _lib.lib()
         self._L = L
         self._h = ctypes.c_void_p()
-        _lib.check(L.ndnlm_plan_create(ctypes.byref(self._h), _lib.i64(self.shape), _lib.u32(self.r), _lib.u32(self.f),
-                                       float(sigma), float(h), float(n_eff), _lib.SEMANTICS[semantics], code,
-                                       _lib.KERNELS[kernel]))
+        rc = -1
+        if dtype == np.float64 and kernel == "auto" and os.environ.get("ND_NLM_FLOAT64_COMPUTE", "").lower() in ("float32", "fp32", "f32"):
+            # opt-in: float64 data through the fp32 tiled kernel (north_star's fp32 compute, ~1e-6 from the float64
+            # result, ~100x the generic float64 kernel); configurations without a tiled instantiation stay generic
+            rc = L.ndnlm_plan_create(ctypes.byref(self._h), _lib.i64(self.shape), _lib.u32(self.r), _lib.u32(self.f),
+                                     float(sigma), float(h), float(n_eff), _lib.SEMANTICS[semantics], code,
+                                     _lib.KERNELS["tiled"])
+        if rc != 0:
+            _lib.check(L.ndnlm_plan_create(ctypes.byref(self._h), _lib.i64(self.shape), _lib.u32(self.r), _lib.u32(self.f),
+                                           float(sigma), float(h), float(n_eff), _lib.SEMANTICS[semantics], code,
+                                           _lib.KERNELS[kernel]))
         info = _lib.Info()
         _lib.check(L.ndnlm_plan_info(self._h, ctypes.byref(info)))
         self.info = info

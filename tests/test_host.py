@@ -76,6 +76,14 @@ def test_plan_kernel_selection():
     assert p64.is_tiled and p64.padded_bytes == (40 + 6) * (50 + 6) * (30 + 4) * 16
     with pytest.raises(ValueError):                                  # V > 8 has no tiled instantiation
         device.Plan((40, 50, 30, 9), (2, 2, 1), (1, 1, 1), 1, 1, kernel="tiled")
+    # ... or globally with ND_NLM_FLOAT64_COMPUTE=float32 (configurations without an instantiation stay generic)
+    os.environ["ND_NLM_FLOAT64_COMPUTE"] = "float32"
+    try:
+        assert device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64).is_tiled
+        assert not device.Plan((40, 50, 30, 9), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64).is_tiled
+        assert device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64, kernel="generic").kernel_name == "nlm_generic<double>"
+    finally:
+        del os.environ["ND_NLM_FLOAT64_COMPUTE"]
 
 
 def test_plan_errors_map_to_reference_exceptions():
