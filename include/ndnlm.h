@@ -134,6 +134,14 @@ int ndnlm_halo_unpack(const ndnlm_plan_t* plan, void* padded, int axis, int side
 int ndnlm_run(const ndnlm_plan_t* plan, const void* padded, void* out_internal,
               int32_t* err_flag, void* stream);
 
+/* Scratch memory some kernels need between their passes (today: the intermediate of the separable box-mean fast
+ * path of NDNLM_REFERENCE_COMPILED; 0 for everything else).  ndnlm_run allocates it stream-ordered on every call
+ * (cudaMallocAsync, slow for multi-GB cubes); ndnlm_run_scratch takes a caller-owned buffer of
+ * ndnlm_scratch_bytes(plan) bytes instead (may be NULL when that is 0). */
+size_t ndnlm_scratch_bytes(const ndnlm_plan_t* plan);
+int ndnlm_run_scratch(const ndnlm_plan_t* plan, const void* padded, void* out_internal,
+                      int32_t* err_flag, void* scratch, void* stream);
+
 /* Unstage: internal output buffer -> strided caller array (the in-place write into `output`). */
 int ndnlm_unstage(const ndnlm_plan_t* plan, const void* out_internal,
                   void* output, const int64_t out_strides[4], void* stream);

@@ -13,6 +13,7 @@
 #include <mutex>
 
 #include "nlm_common.cuh"
+#include "nlm_boxmean.cuh"
 #include "nlm_generic.cuh"
 #include "nlm_staging.cuh"
 using namespace ndnlm;
@@ -119,6 +120,7 @@ struct ndnlm_plan {
     DevParams P;
     int kernel;         // NDNLM_KERNEL_GENERIC / NDNLM_KERNEL_TILED
     int inst;           // index into g_tiled
+    int boxmean;        // reference_compiled fast path (nlm_boxmean.cuh): staged like the tiled kernel, inst == -1
     int threads, grid;
     size_t smem;
     int elem_bytes;
@@ -294,6 +296,12 @@ extern "C" int ndnlm_plan_create(ndnlm_plan_t** out_plan, const int64_t shape[4]
             }
         }
     }
+    // reference_compiled semantics with some f_i > 0 and the default self weight is a reflect box mean:
+    // separable HBM-bound fast path on the tiled staging layout
+    if (kernel != NDNLM_KERNEL_GENERIC && dtype == NDNLM_F32 && P.zero_dist && n_eff < 0 && K > 0 && boxmean_supported(P)) {
+        pl->kernel = NDNLM_KERNEL_TILED;
+        pl->boxmean = 1;
+    }
     if (kernel == NDNLM_KERNEL_TILED && pl->kernel != NDNLM_KERNEL_TILED) {
         delete pl;
         return fail(NDNLM_EINVAL, "no tiled-kernel instantiation for this configuration (dtype/V/f pattern/shared memory)");
@@ -304,7 +312,15 @@ extern "C" int ndnlm_plan_create(ndnlm_plan_t** out_plan, const int64_t shape[4]
         pl->elem_bytes = 4;
         pl->padded_bytes = size_t(pvox) * P.nv4 * 16;
         pl->out_bytes = size_t(voxels) * P.nv4 * 16;
-        snprintf(pl->name, sizeof(pl->name), "%s[passes=%d]", g_tiled[pl->inst].name, P.npass);
+        if (pl->boxmean) {
+            pl->threads = 256;
+            pl->grid = 0;
+            pl->smem = 0;
+            snprintf(pl->name, sizeof(pl->name), "nlm_boxmean<ringW=%d,ringX=%d,rR=%d>[zero_dist]", boxmean_ring_for(P.rad[0]),
+                     boxmean_ring_for(P.rad[2]), P.rad[1]);
+        } else {
+            snprintf(pl->name, sizeof(pl->name), "%s[passes=%d]", g_tiled[pl->inst].name, P.npass);
+        }
     } else {
         pl->elem_bytes = (dtype == NDNLM_F64) ? 8 : 4;
         pl->padded_bytes = size_t(pvox) * V * pl->elem_bytes;
@@ -519,12 +535,30 @@ static encode_tiled_fn get_encode_fn() {
     return fn;
 }
 
+extern "C" size_t ndnlm_scratch_bytes(const ndnlm_plan_t* pl) {
+    if (!pl || !pl->boxmean) return 0;
+    const DevParams& P = pl->P;
+    return size_t(P.n[0] + 2 * P.rad[0]) * P.n[1] * P.n[2] * P.nv4 * sizeof(float4);
+}
+
 extern "C" int ndnlm_run(const ndnlm_plan_t* pl, const void* padded, void* out_internal, int32_t* err_flag, void* stream) {
+    return ndnlm_run_scratch(pl, padded, out_internal, err_flag, nullptr, stream);
+}
+
+extern "C" int ndnlm_run_scratch(const ndnlm_plan_t* pl, const void* padded, void* out_internal, int32_t* err_flag,
+                                 void* scratch, void* stream) {
     if (!pl || !padded || !out_internal || !err_flag) return fail(NDNLM_EINVAL, "null argument");
     GUARD_DEVICE(padded);
     cudaStream_t st = (cudaStream_t)stream;
     const DevParams& P = pl->P;
-    if (pl->kernel == NDNLM_KERNEL_TILED) {
+    if (pl->kernel == NDNLM_KERNEL_TILED && pl->boxmean) {
+        float4* inter = (float4*)scratch;
+        if (!inter) CUDA_TRY(cudaMallocAsync((void**)&inter, ndnlm_scratch_bytes(pl), st));
+        cudaError_t e = boxmean_run(P, (const float4*)padded, (float4*)out_internal, inter, st);
+        g_launches += 2;
+        if (!scratch) cudaFreeAsync(inter, st);
+        if (e != cudaSuccess) return fail(NDNLM_ECUDA, "box-mean kernels failed to launch: %s", cudaGetErrorString(e));
+    } else if (pl->kernel == NDNLM_KERNEL_TILED) {
         const TiledInst& ti = g_tiled[pl->inst];
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
@@ -564,7 +598,7 @@ static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 extern "C" size_t ndnlm_workspace_bytes(const ndnlm_plan_t* pl) {
     if (!pl) return 0;
-    return align256(pl->padded_bytes) + align256(pl->out_bytes) + 256;
+    return align256(pl->padded_bytes) + align256(pl->out_bytes) + 256 + align256(ndnlm_scratch_bytes(pl));
 }
 
 extern "C" int ndnlm_apply(const ndnlm_plan_t* pl, const void* arr, const int64_t arr_strides[4], void* output,
@@ -579,7 +613,8 @@ extern "C" int ndnlm_apply(const ndnlm_plan_t* pl, const void* arr, const int64_
     CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
     int rc = ndnlm_stage(pl, arr, arr_strides, padded, -1, NDNLM_EDGE_REFLECT, NDNLM_EDGE_REFLECT, stream);
     if (rc) return rc;
-    rc = ndnlm_run(pl, padded, internal, flag, stream);
+    void* scratch = ndnlm_scratch_bytes(pl) ? (void*)(ws + align256(pl->padded_bytes) + align256(pl->out_bytes) + 256) : nullptr;
+    rc = ndnlm_run_scratch(pl, padded, internal, flag, scratch, stream);
     if (rc) return rc;
     rc = ndnlm_unstage(pl, internal, output, out_strides, stream);
     if (rc) return rc;

@@ -64,6 +64,8 @@ class Plan:
         self.flops_per_voxel = float(info.flops_per_voxel)
         self.voxels = int(info.voxels)
         self.n_offsets = int(info.n_offsets)
+        self.scratch_bytes = int(L.ndnlm_scratch_bytes(self._h))
+        self._scratch = None
 
     def __del__(self):
         try:
@@ -122,9 +124,17 @@ class Plan:
         _lib.check(self._L.ndnlm_halo_unpack(self._h, ctypes.c_void_p(padded.data_ptr()), int(axis), int(side),
                                              ctypes.c_void_p(msg.data_ptr()), self._stream(padded)))
 
-    def run(self, padded, internal_out, err_flag):
-        _lib.check(self._L.ndnlm_run(self._h, ctypes.c_void_p(padded.data_ptr()), ctypes.c_void_p(internal_out.data_ptr()),
-                                     ctypes.c_void_p(err_flag.data_ptr()), self._stream(padded)))
+    def run(self, padded, internal_out, err_flag, scratch=None):
+        if scratch is None and self.scratch_bytes:
+            # kept with the plan: stream-ordered reuse on the current stream (callers running one plan on several
+            # streams at once pass their own scratch)
+            if self._scratch is None or self._scratch.device != padded.device:
+                self._scratch = torch.empty(self.scratch_bytes, dtype=torch.uint8, device=padded.device)
+            scratch = self._scratch
+        _lib.check(self._L.ndnlm_run_scratch(self._h, ctypes.c_void_p(padded.data_ptr()),
+                                             ctypes.c_void_p(internal_out.data_ptr()), ctypes.c_void_p(err_flag.data_ptr()),
+                                             ctypes.c_void_p(scratch.data_ptr() if scratch is not None else None),
+                                             self._stream(padded)))
 
     def unstage(self, internal_out, output):
         self._check_arr(output)
@@ -150,6 +160,19 @@ def synth_cube(ny_local, nx, nt, V=4, y_offset=0, seed=42, device="cuda"):
     out = torch.empty((ny_local, nx, nt, V), dtype=torch.float32, device=device)
     with torch.cuda.device(out.device):
         _lib.check(_lib.lib().ndnlm_synth_cube(ctypes.c_void_p(out.data_ptr()), ny_local, nx, nt, V, y_offset, seed,
+                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
+
+
+def synth_cube_into(out, y_offset=0, seed=42):
+    """Fill the contiguous float32 device tensor `out` (rows, nx, nt, V) with rows [y_offset, y_offset + rows) of the
+    synthetic cube (the same generator as `synth_cube`, keyed by GLOBAL index: slabs, shards and crops of the
+    same cube agree wherever they overlap)."""
+    if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.dim() == 4):
+        raise ValueError("expected a contiguous float32 CUDA tensor (rows, nx, nt, V)")
+    ny, nx, nt, V = (int(x) for x in out.shape)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().ndnlm_synth_cube(ctypes.c_void_p(out.data_ptr()), ny, nx, nt, V, int(y_offset), int(seed),
                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return out
 

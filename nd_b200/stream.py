@@ -39,9 +39,15 @@ def can_pipeline(arr, output, min_rows=64):
             and dense_axis_order(arr) is not None and dense_axis_order(arr) == dense_axis_order(output))
 
 
-def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None, kernel='auto', slab_rows=None):
+def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None, kernel='auto', slab_rows=None,
+                         copy_only=False, row_range=None):
     """Filter host array `arr` into host array `output` through the slab pipeline.  Raises
-    ValueError('No solution') like the reference when find_weight fails anywhere."""
+    ValueError('No solution') like the reference when find_weight fails anywhere.
+
+    row_range=(lo, hi) restricts the work to rows [lo, hi) of axis 0 (the rows outside are still read as the
+    buffer of the first / last slab): one GPU's share of a multi-GPU apply over a host array.
+    copy_only=True runs the same slabs, streams and copies WITHOUT the kernels (the filtered rows are a device
+    copy of the input): the host-memory / PCIe ceiling of this pipeline, reported by bench.py beside `e2e`."""
     order = dense_axis_order(arr)
     if order is None or order != dense_axis_order(output):
         raise ValueError('apply_host_pipelined needs dense arrays with identical memory layout')
@@ -60,7 +66,12 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
             tile0 = int(probe.info.tile[list(probe.info.role_axis).index(0)])
             if tile0 > 0:
                 slab_rows = max(tile0, slab_rows // tile0 * tile0)
-    sp = ShardPlan.from_rows(n0, slab_rows, halo)
+    r_lo, r_hi = (0, n0) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    if not (0 <= r_lo < r_hi <= n0):
+        raise ValueError('row_range must lie inside the array')
+    sp = ShardPlan.from_rows(r_hi - r_lo, slab_rows, halo)
+    sp.ranges = [(lo + r_lo, hi + r_lo) for lo, hi in sp.ranges]
+    sp.n = n0            # buffered_range clips against the whole array, not the row range
 
     # host views in memory order: hv[outer..., rows, inner...] with every [outer][lo:hi] block contiguous
     k0 = order.index(0)
@@ -121,9 +132,12 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
             plan = plans[(hi - lo,) + tuple(arr.shape[1:])]
             a_in = block(d_in[b], lo - blo, hi - blo).permute(inv)     # logical (rows, N1, N2, V) view of the interior
             a_out = block(d_out[b], 0, hi - lo).permute(inv)
-            plan.stage(a_in, padded[b], 0, 'reflect' if lo == 0 else 'source', 'reflect' if hi == n0 else 'source')
-            plan.run(padded[b], internal[b], flag)
-            plan.unstage(internal[b], a_out)
+            if copy_only:
+                a_out.copy_(a_in)
+            else:
+                plan.stage(a_in, padded[b], 0, 'reflect' if lo == 0 else 'source', 'reflect' if hi == n0 else 'source')
+                plan.run(padded[b], internal[b], flag)
+                plan.unstage(internal[b], a_out)
             ev_comp = torch.cuda.Event()
             ev_comp.record(s_comp)
             ev_in_free[b] = ev_comp
@@ -136,6 +150,80 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
     for s in (s_h2d, s_comp, s_d2h):
         cur.wait_stream(s)
     cur.synchronize()
+    if int(flag.item()):
+        raise ValueError('No solution')
+    return sp.nshards
+
+
+def apply_device_streamed(source, sink, n0, inner_shape, r3, f3, sigma, h, n_eff=-1, semantics=None, kernel='auto',
+                          slab_rows=None, lo_rows=None, hi_rows=None, dtype=np.float32, on_kernel=None):
+    """Filter a cube of `n0` rows that is PRODUCED and CONSUMED slab by slab on the device -- cubes (or y-shards
+    of cubes) whose input + staged copy + result do not fit in HBM at once (BASELINE configs[3] on 2 / 4 GPUs,
+    configs[4] anywhere).  Same 1-D split with an `r+f` buffer as the host pipeline above (the reference's
+    `xr_split` rule, nd/utils.py:288-340); every slab is staged from its buffered rows (NDNLM_EDGE_SOURCE), so
+    nothing is computed twice and the result is bitwise the unsliced call.
+
+    source(lo, hi, out)    fills the contiguous device tensor `out` (hi-lo, N1, N2, V) with rows [lo, hi) of the cube
+    sink(lo, hi, result)   consumes the filtered rows [lo, hi) (device tensor, valid until the next slab)
+    lo_rows / hi_rows      (r0+f0, N1, N2, V) device tensors: the rows just below row 0 / just above row n0-1 when the
+                           cube is a y-shard of a larger one (exchanged with the neighbouring GPUs beforehand);
+                           None = the cube really ends there and is reflected (reference `_idx`, nd/_filters.pyx:34-40)
+    on_kernel(a, b)        optional hook called around every kernel launch (bench.py records CUDA events there)
+    Returns the number of slabs.  Raises ValueError('No solution') like the reference."""
+    n0 = int(n0)
+    inner_shape = tuple(int(x) for x in inner_shape)
+    halo = int(r3[0]) + int(f3[0])
+    device = torch.device('cuda', torch.cuda.current_device())
+    tdtype = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    itemsize = np.dtype(dtype).itemsize
+    for nb in (lo_rows, hi_rows):
+        if nb is not None and tuple(nb.shape) != (halo,) + inner_shape:
+            raise ValueError('neighbour rows must have shape %s' % ((halo,) + inner_shape,))
+    if slab_rows is None:
+        row_bytes = itemsize * int(np.prod(inner_shape))
+        slab_rows = max(4 * halo + 16, min(n0, (4 << 30) // max(row_bytes, 1)))
+    slab_rows = min(int(slab_rows), n0)
+    probe = dev.Plan((max(slab_rows, halo + 1),) + inner_shape, r3, f3, sigma, h, n_eff, semantics=semantics,
+                     dtype=dtype, kernel=kernel)
+    if probe.is_tiled and slab_rows < n0:
+        tile0 = int(probe.info.tile[list(probe.info.role_axis).index(0)])
+        if tile0 > 0:
+            slab_rows = max(tile0, slab_rows // tile0 * tile0)
+    sp = ShardPlan.from_rows(n0, slab_rows, halo)
+    max_int = max(hi - lo for lo, hi in sp.ranges)
+    d_in = torch.empty((max_int + 2 * halo,) + inner_shape, dtype=tdtype, device=device)
+    d_out = torch.empty((max_int,) + inner_shape, dtype=tdtype, device=device)
+    plans = {}
+    for lo, hi in sp.ranges:
+        if hi - lo not in plans:
+            plans[hi - lo] = dev.Plan((hi - lo,) + inner_shape, r3, f3, sigma, h, n_eff, semantics=semantics,
+                                      dtype=dtype, kernel=kernel)
+    padded = torch.empty(max(p.padded_bytes for p in plans.values()), dtype=torch.uint8, device=device)
+    internal = torch.empty(max(p.out_bytes for p in plans.values()), dtype=torch.uint8, device=device)
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    for lo, hi in sp.ranges:
+        # rows below: the neighbour shard's rows at the shard edge, rows of this cube otherwise (none at a true edge)
+        below = halo if (lo > 0 or lo_rows is not None) else 0
+        above = halo if (hi < n0 or hi_rows is not None) else 0
+        own_lo, own_hi = max(lo - below, 0), min(hi + above, n0)
+        off = below - (lo - own_lo)              # rows taken from lo_rows
+        if off > 0:
+            d_in[:off].copy_(lo_rows[halo - off:])
+        source(own_lo, own_hi, d_in[off:off + own_hi - own_lo])
+        top = above - (own_hi - hi)              # rows taken from hi_rows
+        if top > 0:
+            d_in[off + own_hi - own_lo:off + own_hi - own_lo + top].copy_(hi_rows[:top])
+        plan = plans[hi - lo]
+        a_in = d_in[below:below + hi - lo]
+        a_out = d_out[:hi - lo]
+        plan.stage(a_in, padded, 0, 'source' if below else 'reflect', 'source' if above else 'reflect')
+        if on_kernel is not None:
+            on_kernel(True, plan)
+        plan.run(padded, internal, flag)
+        if on_kernel is not None:
+            on_kernel(False, plan)
+        plan.unstage(internal, a_out)
+        sink(lo, hi, a_out)
     if int(flag.item()):
         raise ValueError('No solution')
     return sp.nshards

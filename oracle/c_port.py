@@ -30,12 +30,13 @@ def _load():
             fn.restype = ctypes.c_int
             fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                            ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
-                           ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+                           ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
     return _lib
 
 
-def nlmeans(arr, r, f, sigma, h, n_eff=-1, semantics="as_written", threads=None):
-    """Run the C restatement on a (N0,N1,N2,V) float32/float64 array (any strides)."""
+def nlmeans(arr, r, f, sigma, h, n_eff=-1, semantics="as_written", threads=None, roi=None):
+    """Run the C restatement on a (N0,N1,N2,V) float32/float64 array (any strides).
+    roi = ((a0, a1), (b0, b1), (c0, c1)): compute only the output voxels of that box (the rest stays 0)."""
     L = _load()
     arr = np.asarray(arr)
     if arr.dtype not in (np.float32, np.float64):
@@ -49,7 +50,8 @@ def nlmeans(arr, r, f, sigma, h, n_eff=-1, semantics="as_written", threads=None)
     fn = L.nlm_oracle_f32 if arr.dtype == np.float32 else L.nlm_oracle_f64
     rc = fn(arr.ctypes.data, out.ctypes.data, I64(*arr.shape), I64(*[s // it for s in arr.strides]),
             I64(*[s // it for s in out.strides]), U32(*[int(x) for x in r]), U32(*[int(x) for x in f]),
-            float(sigma), float(h), float(n_eff), 1 if semantics == "reference_compiled" else 0)
+            float(sigma), float(h), float(n_eff), 1 if semantics == "reference_compiled" else 0,
+            (ctypes.c_int64 * 6)(*[int(v) for ab in roi for v in ab]) if roi is not None else None)
     if rc:
         raise ValueError("No solution")
     return out

@@ -17,6 +17,8 @@
  *
  * Strides are in ELEMENTS.  Returns 0, or 1 if find_weight had no solution (the reference raises
  * ValueError('No solution') at that voxel; here the scan stops there as well).
+ * `roi` (may be NULL) restricts the OUTPUT voxels to the box [roi[0],roi[1]) x [roi[2],roi[3]) x [roi[4],roi[5]);
+ * the arithmetic of every computed voxel is unchanged (bench.py uses it to check sampled sub-cubes of a large cube).
  * Build: gcc -O3 -fopenmp -shared -fPIC nlm_oracle.c -o libnlm_oracle.so -lm  (OpenMP only splits
  * the outermost voxel loop; every voxel is computed exactly as in the serial reference.)
  */
@@ -33,16 +35,18 @@ static inline int64_t idx_reflect(int64_t i, int64_t n) { /* nd/_filters.pyx:34-
 #define DEFINE_ORACLE(NAME, T)                                                                          \
     int NAME(const T* arr, T* out, const int64_t shape[4], const int64_t as[4], const int64_t os[4],     \
              const uint32_t r[3], const uint32_t f[3], double sigma, double h, double n_eff,             \
-             int compiled_bug) {                                                                         \
+             int compiled_bug, const int64_t* roi) {                                                     \
         const int64_t N0 = shape[0], N1 = shape[1], N2 = shape[2], V = shape[3];                        \
         const T dsq_norm = (T)(V * (2 * (int64_t)f[0] + 1) * (2 * (int64_t)f[1] + 1) * (2 * (int64_t)f[2] + 1)); \
         const int skip_patch = compiled_bug && (f[0] > 0 || f[1] > 0 || f[2] > 0);                       \
         int failed = 0;                                                                                  \
+        const int64_t a0 = roi ? roi[0] : 0, a1 = roi ? roi[1] : N0, b0 = roi ? roi[2] : 0,              \
+                      b1 = roi ? roi[3] : N1, c0 = roi ? roi[4] : 0, c1 = roi ? roi[5] : N2;             \
         _Pragma("omp parallel for schedule(dynamic, 1)")                                                 \
-        for (int64_t p0 = 0; p0 < N0 * N1; ++p0) {                                                       \
-            const int64_t pa = p0 / N1, pb = p0 % N1;                                                    \
+        for (int64_t p0 = 0; p0 < (a1 - a0) * (b1 - b0); ++p0) {                                         \
+            const int64_t pa = a0 + p0 / (b1 - b0), pb = b0 + p0 % (b1 - b0);                            \
             T* wsum = (T*)malloc(sizeof(T) * (size_t)V);                                                 \
-            for (int64_t pc = 0; pc < N2 && !failed; ++pc) {                                             \
+            for (int64_t pc = c0; pc < c1 && !failed; ++pc) {                                            \
                 double total_w = 0, total_sq = 0, max_w = 0;                                             \
                 for (int64_t v = 0; v < V; ++v) wsum[v] = 0;                                             \
                 for (int64_t qa = pa - r[0]; qa <= pa + (int64_t)r[0]; ++qa)                             \

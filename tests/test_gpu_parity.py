@@ -125,12 +125,27 @@ def test_float64_data_on_the_fp32_tiled_kernel_on_request(dev, c_oracle, shape, 
     assert np.array_equal(out.astype(np.float32), out32)          # exactly the float32 path
 
 
-@pytest.mark.parametrize("shape,r,f", [CASES[0], CASES[4], CASES[10]])
+@pytest.mark.parametrize("shape,r,f", [CASES[0], CASES[1], CASES[3], CASES[4], CASES[5], CASES[7], CASES[10], CASES[11],
+                                       CASES[14], CASES[15], ((40, 300, 70, 4), (5, 5, 2), (1, 1, 1)),
+                                       ((9, 40, 11, 4), (4, 6, 4), (1, 1, 1))])
 def test_reference_compiled_semantics(dev, c_oracle, shape, r, f):
+    """Bug-for-bug the LP64 binary: a reflect box mean.  float32 data with the default self weight
+    runs on the separable box-mean fast path (nlm_boxmean.cuh), whose float32 sums are ordered differently from
+    the reference's sequential float32 accumulation: agreement to rounding noise, not bitwise."""
     a = sar_like(shape, seed=4, dtype=np.float32)
-    ref = c_oracle.nlmeans(a, r, f, 0.3, 0.6, semantics="reference_compiled")
+    ref = c_oracle.nlmeans(a, r, f, 0.3, 0.6, semantics="reference_compiled", threads=8)
     out, plan = run_plan(dev, a, r, f, 0.3, 0.6, semantics="reference_compiled")
-    assert scaled_err(out, ref) < 3e-6, plan.kernel_name
+    assert "boxmean" in plan.kernel_name, plan.kernel_name
+    assert scaled_err(out, ref) < 1e-5, plan.kernel_name
+    out_g, plan_g = run_plan(dev, a, r, f, 0.3, 0.6, semantics="reference_compiled", kernel="generic")
+    assert "generic" in plan_g.kernel_name and scaled_err(out_g, ref) < 3e-6
+
+
+def test_reference_compiled_neff_stays_on_the_generic_kernel(dev, c_oracle):
+    a = sar_like((10, 16, 7, 4), seed=8, dtype=np.float32)
+    ref = c_oracle.nlmeans(a, (2, 2, 1), (1, 1, 1), 0.3, 0.6, n_eff=6.0, semantics="reference_compiled")
+    out, plan = run_plan(dev, a, (2, 2, 1), (1, 1, 1), 0.3, 0.6, n_eff=6.0, semantics="reference_compiled")
+    assert "generic" in plan.kernel_name and scaled_err(out, ref) < 3e-6
 
 
 def test_neff(dev, c_oracle):
