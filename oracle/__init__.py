@@ -28,6 +28,8 @@ Oracles of the rows built after the hot path:
 4. `oracle.ndimage_numpy`  -- NumPy restatement of the scipy.ndimage arithmetic below the sibling
                               filters (row N2).  PINNED: bit-exact against scipy itself on the CPU
                               (`tests/test_sibling_filters.py`); the GPU tests then use scipy directly.
-5. `oracle.omnibus_oracle` -- NumPy restatement of `nd/_change.pyx` (row N4).  PARITY UNPINNED: the
-                              reference needs GSL, which is not installed, so it cannot be run here.
+5. `oracle.omnibus_oracle` -- NumPy restatement of `nd/_change.pyx` (row N4).  PINNED: `oracle.ref_change` wraps the
+                              reference's own `_change.pyx`, compiled unmodified into `oracle/_ref/_change` with
+                              `oracle/gsl_shim` standing in for its one GSL call (chi-square CDF; checked against
+                              published table values); golden vectors `tests/golden/change_golden.npz`.
 """

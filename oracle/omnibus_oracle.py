@@ -5,11 +5,14 @@ TEST INFRASTRUCTURE ONLY.  NumPy restatement of the reference's omnibus change d
 reference's typing: `floating` locals take the dtype of the data (float32 or float64), `prod_of_dets` / `logQ`
 and the constants are double.
 
-PARITY UNPINNED: the reference evaluates the chi-square CDF with GSL (`cython_gsl.gsl_cdf_chisq_P`, :155-156).
-GSL is not installed in this image, so the reference's `_change` extension cannot be built and there are no golden
-vectors; here the CDF is `scipy.special.gammainc(f/2, z/2)` -- the function the reference's own deprecated
-`array_omnibus` uses (`scipy.stats.chi2.cdf`, :124-125).  The two agree to ~1e-15; a decision `p > alpha` could
-differ only for a probability within that distance of alpha.
+PARITY PINNED (round 2): the reference's own nd/_change.pyx is compiled UNMODIFIED into oracle/_ref/_change by
+oracle/build_ref.py; its only third-party call, `cython_gsl.gsl_cdf_chisq_P` (:147-148; GSL is not installed and
+the reference pins no version), is supplied by the stand-in oracle/gsl_shim (the published regularised incomplete
+gamma function, checked against chi-square tables and scipy).  tests/test_oracle_change.py compares this
+restatement with outputs of that binary (tests/golden/change_golden.npz): probabilities to 1e-13, change maps
+exactly.  Here the CDF is `scipy.special.gammainc(f/2, z/2)` -- what the reference's own deprecated `array_omnibus`
+uses (`scipy.stats.chi2.cdf`, :124-125); shim, scipy and GSL agree to ~1e-15, so a decision `p > alpha` could differ
+only for a probability within that distance of alpha.
 """
 import numpy as np
 from scipy.special import gammainc

@@ -2,10 +2,11 @@
 Omnibus change detection: the CUDA kernels behind include/ndchg.h against the NumPy
 restatement of nd/_change.pyx in oracle/omnibus_oracle.py.
 
-PARITY UNPINNED (stated in the oracle's header and DESIGN.md): the reference evaluates the chi-square CDF with GSL,
-which is not installed here, so the reference's extension cannot be built; the oracle uses scipy's incomplete gamma
-function (what the reference's own `array_omnibus` uses).  Bars: probabilities within 1e-12 (float64 data) /
-2e-6 (float32 data: the statistic itself is rounded to float32 like in the reference); change maps identical.
+PARITY PINNED: tests/golden/change_golden.npz holds outputs of the reference's OWN nd/_change.pyx, compiled
+unmodified against a stand-in for its only third-party call, `gsl_cdf_chisq_P` (oracle/gsl_shim, checked against
+published chi-square tables and scipy in tests/test_oracle_change.py); the NumPy restatement is pinned to the same
+file there.  Bars: probabilities within 1e-12 (float64 data) / 2e-6 (float32 data: the statistic itself is rounded
+to float32 like in the reference); change maps identical.
 """
 import inspect
 import os
@@ -105,6 +106,22 @@ def test_change_maps_equal_oracle(dtype):
         assert got.dtype == np.uint8 and got.shape == (8, 9, k)
         assert np.array_equal(got, ref), (k, looks, alpha, int((got != ref).sum()))
         assert ref.sum() > 0
+
+
+@pytest.mark.gpu
+def test_golden_from_the_compiled_reference():
+    """CUDA kernels against outputs of the reference's own compiled nd/_change.pyx (tests/golden/make_change_golden.py)."""
+    import json
+    z = np.load(os.path.join(ROOT, "tests", "golden", "change_golden.npz"))
+    meta = json.loads(str(z["__meta__"]))
+    for name, m in meta.items():
+        v = z[name + "__in"]
+        got = change.change_detection(v, alpha=m["alpha"], n=m["n"])
+        assert np.array_equal(got, z[name + "__change"]), (name, int((got != z[name + "__change"]).sum()))
+        prob = change.omnibus_probability(v, n=m["n"])
+        tol = 1e-12 if v.dtype == np.float64 else 2e-6
+        assert np.abs(prob.astype(np.float64) - z[name + "__prob"].astype(np.float64)).max() < tol, name
+        assert m["changes"] > 0
 
 
 @pytest.mark.gpu
