@@ -375,7 +375,7 @@ def run_ours(args):
     streamed = wl["mode"] == "streamed"
     pk = peaks()
     if streamed:
-        global_rows = wl["global_rows"]
+        global_rows = args.global_rows or wl["global_rows"]
         shard_rows = global_rows // world                 # rows of the global cube this rank owns
         ny = min(args.rows, shard_rows) if args.rows else shard_rows    # rows it actually processes
         y_lo = rank * shard_rows
@@ -748,6 +748,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--semantics", default="as_written", choices=["as_written", "reference_compiled"])
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU actually processed (cfg4/cfg5: partial sweep)")
+    ap.add_argument("--global-rows", type=int, default=0,
+                    help="development: height of the global cube of a streamed workload (default: the configuration's)")
     ap.add_argument("--apply-njobs", type=int, default=0, help="bench NLMeansFilter.apply(ds, njobs=N) in one process")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -98,6 +98,17 @@ int ndnlm_plan_create(ndnlm_plan_t** plan, const int64_t shape[4],
                       const uint32_t r[3], const uint32_t f[3],
                       double sigma, double h, double n_eff,
                       int semantics, int dtype, int kernel);
+/*
+ * The same with the role assignment given by the caller: role_axis[k] = user axis (0..2) that plays role
+ * W, R, X (k = 0, 1, 2), as reported by ndnlm_plan_info of another plan; NULL = choose from the shape.
+ * ndnlm_plan_create chooses the X / R roles from the extents of axes 1 and 2, so the shards of an array cut along
+ * axis 1 or 2 could otherwise end up with different staged layouts than their neighbours (their halo messages
+ * would be mis-read); a sharding driver creates the plan of the WHOLE array first and hands its roles to every shard.
+ */
+int ndnlm_plan_create_roles(ndnlm_plan_t** plan, const int64_t shape[4],
+                            const uint32_t r[3], const uint32_t f[3],
+                            double sigma, double h, double n_eff,
+                            int semantics, int dtype, int kernel, const int32_t* role_axis);
 void ndnlm_plan_destroy(ndnlm_plan_t* plan);
 int  ndnlm_plan_info(const ndnlm_plan_t* plan, ndnlm_info_t* info);
 

@@ -44,7 +44,9 @@ def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=No
     semantics   : 'as_written' (default) or 'reference_compiled' (SURVEY.md D1); also ND_NLM_SEMANTICS.
     njobs       : number of GPUs to shard over along `shard_axis` (default: the largest axis that is
                   not filtered, else the largest axis -- reference nd/filters.py:424-435).
-    pipeline    : stream host arrays through the GPU in slabs with overlapped copies (default: arrays >= 256 MiB).
+    pipeline    : stream host arrays through the GPU in slabs with overlapped copies (default: arrays >= 256 MiB;
+                  with njobs > 1: one slab pipeline per GPU whenever the shards run along axis 0 -- False keeps the
+                  shards resident on the devices and exchanges their halo rows over NVLink peer copies).
     devices     : optional explicit CUDA device index per shard (e.g. [0, 0] exercises the shard /
                   halo-exchange layer on a single GPU).
     """
@@ -76,7 +78,7 @@ def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=No
     if devices is not None:
         njobs = len(devices)
     if njobs > 1 or devices is not None:
-        _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis, devices)
+        _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis, devices, pipeline)
         return
 
     # large host arrays: slab pipeline (H2D / kernels / D2H overlapped), nd_b200/stream.py
@@ -103,10 +105,28 @@ def _copy_back(output, d_out):
         output[...] = d_out.cpu().numpy()
 
 
-def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis, devices=None):
-    """Single-process multi-GPU apply: shard along one axis, halo rows over NVLink peer copies."""
+def choose_shard_axis(shape, r3, f3, njobs):
+    """The reference's rule (`NLMeansFilter._parallel_dimension`, nd/filters.py:424-435): the largest axis that is
+    not filtered, else the largest axis -- but an unfiltered axis too short to give every job a row (the usual 2-D
+    case: a leading axis of extent 1) is no use, so only unfiltered axes with at least `njobs` rows qualify."""
+    free = [a for a in range(3) if r3[a] == 0 and f3[a] == 0 and shape[a] >= njobs]
+    cand = free if free else [a for a in range(3) if r3[a] > 0 or f3[a] > 0] or [0, 1, 2]
+    return max(cand, key=lambda a: shape[a])
+
+
+def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, shard_axis, devices=None, pipeline=None):
+    """Single-process multi-GPU apply over a HOST array (`njobs` = GPUs).
+
+    Shards along axis 0 of a dense array are streamed: one slab pipeline per GPU (nd_b200/stream.py), each driven by
+    its own thread, reading the `r+f` buffer rows of its neighbours straight from the host array -- the reference's
+    own scheme (`xr_split` hands every worker its chunk plus a buffer, nd/utils.py:288-340), so no GPU-to-GPU
+    exchange is needed.  Other shard axes / layouts keep their shards resident on the devices and exchange halo rows
+    over NVLink peer copies."""
+    import threading
+    import warnings
     import torch
     from . import device as dev
+    from . import stream as _stream
     from .shard import ShardPlan, exchange_halos_p2p
 
     ndev = torch.cuda.device_count()
@@ -116,18 +136,48 @@ def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, sha
         devices = list(range(njobs))
     devices = [int(d) for d in devices]
     if shard_axis is None:
-        free = [a for a in range(3) if r3[a] == 0 and f3[a] == 0]
-        cand = free if free else [0, 1, 2]
-        shard_axis = max(cand, key=lambda a: arr.shape[a])
+        shard_axis = choose_shard_axis(arr.shape, r3, f3, njobs)
     halo = r3[shard_axis] + f3[shard_axis]
     sp = ShardPlan(arr.shape[shard_axis], njobs, halo)
+    if sp.nshards < njobs:
+        warnings.warn('axis %d (%d rows, halo %d) carries only %d of the %d requested shards'
+                      % (shard_axis, arr.shape[shard_axis], halo, sp.nshards, njobs))
+    devices = devices[:sp.nshards]
+
+    if (pipeline is not False and shard_axis == 0 and _stream.can_pipeline(arr, output, min_rows=1)
+            and min(hi - lo for lo, hi in sp.ranges) >= 8 * max(halo, 1)):
+        errors = []
+
+        def worker(i):
+            try:
+                torch.cuda.set_device(devices[i])
+                _stream.apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff, semantics=semantics, kernel=kernel,
+                                             row_range=sp.ranges[i])
+            except BaseException as e:          # re-raised in the caller's thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(i,)) for i in range(sp.nshards)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return
+
+    # every shard uses the staged layout (role assignment, kernel) of the whole array: the halo messages of
+    # neighbouring shards must mean the same rows
+    whole = dev.Plan(arr.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)
     plans, paddeds, outs, flags, slabs = [], [], [], [], []
     for i, (lo, hi) in enumerate(sp.ranges):
         idx = [slice(None)] * 4
         idx[shard_axis] = slice(lo, hi)
         slab = arr[tuple(idx)]
         with torch.cuda.device(devices[i]):
-            plan = dev.Plan(slab.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)
+            plan = dev.Plan(slab.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype,
+                            kernel='tiled' if whole.is_tiled else 'generic', roles=whole.roles)
+            if plan.roles != whole.roles or plan.is_tiled != whole.is_tiled:
+                raise RuntimeError('shard %d would use another staged layout than the whole array' % i)
             d_in = torch.from_numpy(slab).to('cuda:%d' % devices[i], non_blocking=True)
             padded = plan.new_padded(d_in.device)
             lo_e, hi_e = sp.edges(i)

@@ -22,7 +22,7 @@ KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "tiled": KERNEL_TILED
 
 # every symbol include/ndnlm.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "ndnlm_plan_create", "ndnlm_plan_destroy", "ndnlm_plan_info", "ndnlm_stage", "ndnlm_halo_bytes",
+    "ndnlm_plan_create", "ndnlm_plan_create_roles", "ndnlm_plan_destroy", "ndnlm_plan_info", "ndnlm_stage", "ndnlm_halo_bytes",
     "ndnlm_halo_pack", "ndnlm_halo_unpack", "ndnlm_run", "ndnlm_run_scratch", "ndnlm_scratch_bytes", "ndnlm_unstage", "ndnlm_workspace_bytes",
     "ndnlm_apply", "ndnlm_synth_cube", "ndnlm_measure_fp32_peak", "ndnlm_launch_count", "ndnlm_last_error", "ndnlm_version",
 ]
@@ -73,6 +73,10 @@ def lib():
     L.ndnlm_plan_create.argtypes = [ctypes.POINTER(vp), i64p, u32p, u32p, ctypes.c_double, ctypes.c_double,
                                     ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.ndnlm_plan_create.restype = ctypes.c_int
+    L.ndnlm_plan_create_roles.argtypes = [ctypes.POINTER(vp), i64p, u32p, u32p, ctypes.c_double, ctypes.c_double,
+                                          ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_int32)]
+    L.ndnlm_plan_create_roles.restype = ctypes.c_int
     L.ndnlm_plan_destroy.argtypes = [vp]
     L.ndnlm_plan_destroy.restype = None
     L.ndnlm_plan_info.argtypes = [vp, ctypes.POINTER(Info)]

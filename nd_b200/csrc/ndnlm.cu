@@ -196,7 +196,19 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti) {
 extern "C" int ndnlm_plan_create(ndnlm_plan_t** out_plan, const int64_t shape[4], const uint32_t r[3],
                                  const uint32_t f[3], double sigma, double h, double n_eff, int semantics,
                                  int dtype, int kernel) {
+    return ndnlm_plan_create_roles(out_plan, shape, r, f, sigma, h, n_eff, semantics, dtype, kernel, nullptr);
+}
+
+extern "C" int ndnlm_plan_create_roles(ndnlm_plan_t** out_plan, const int64_t shape[4], const uint32_t r[3],
+                                       const uint32_t f[3], double sigma, double h, double n_eff, int semantics,
+                                       int dtype, int kernel, const int32_t* role_axis) {
     if (!out_plan || !shape || !r || !f) return fail(NDNLM_EINVAL, "null argument");
+    if (role_axis) {
+        int seen = 0;
+        for (int k = 0; k < 3; ++k)
+            if (role_axis[k] >= 0 && role_axis[k] <= 2) seen |= 1 << role_axis[k];
+        if (seen != 7) return fail(NDNLM_EINVAL, "role_axis must be a permutation of (0, 1, 2)");
+    }
     *out_plan = nullptr;
     if (dtype != NDNLM_F32 && dtype != NDNLM_F64)
         return fail(NDNLM_EDTYPE, "No matching signature found (only float32 / float64 data is supported)");
@@ -242,6 +254,9 @@ extern "C" int ndnlm_plan_create(ndnlm_plan_t** out_plan, const int64_t shape[4]
         ar = -1;
         for (int a = 2; a >= 0; --a) if (a != ax && ar < 0) ar = a;
         aw = 3 - ax - ar;
+    }
+    if (role_axis) {   // roles fixed by the caller: every shard of one array must use the layout of the whole
+        aw = role_axis[ROLE_W]; ar = role_axis[ROLE_R]; ax = role_axis[ROLE_X];
     }
     pl->perm[ROLE_W] = aw; pl->perm[ROLE_R] = ar; pl->perm[ROLE_X] = ax;
 

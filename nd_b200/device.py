@@ -19,7 +19,7 @@ def default_semantics():
 class Plan:
     """One (shape, r, f, sigma, h, n_eff, semantics, dtype) configuration (ndnlm_plan_create)."""
 
-    def __init__(self, shape, r, f, sigma, h, n_eff=-1, semantics=None, dtype=np.float32, kernel="auto"):
+    def __init__(self, shape, r, f, sigma, h, n_eff=-1, semantics=None, dtype=np.float32, kernel="auto", roles=None):
         dtype = np.dtype(dtype)
         if dtype == np.float32:
             code = _lib.F32
@@ -44,20 +44,24 @@ class Plan:
         self._L = L
         self._h = ctypes.c_void_p()
         rc = -1
+        # roles = (axis of W, axis of R, axis of X) taken from the plan of the WHOLE array when this plan is one of
+        # its shards (ndnlm_plan_create_roles); None = chosen from the shape
+        role_arg = (ctypes.c_int32 * 3)(*[int(a) for a in roles]) if roles is not None else None
         if dtype == np.float64 and kernel == "auto" and os.environ.get("ND_NLM_FLOAT64_COMPUTE", "").lower() in ("float32", "fp32", "f32"):
             # opt-in: float64 data through the fp32 tiled kernel (north_star's fp32 compute, ~1e-6 from the float64
             # result, ~100x the generic float64 kernel); configurations without a tiled instantiation stay generic
-            rc = L.ndnlm_plan_create(ctypes.byref(self._h), _lib.i64(self.shape), _lib.u32(self.r), _lib.u32(self.f),
-                                     float(sigma), float(h), float(n_eff), _lib.SEMANTICS[semantics], code,
-                                     _lib.KERNELS["tiled"])
-        if rc != 0:
-            _lib.check(L.ndnlm_plan_create(ctypes.byref(self._h), _lib.i64(self.shape), _lib.u32(self.r), _lib.u32(self.f),
+            rc = L.ndnlm_plan_create_roles(ctypes.byref(self._h), _lib.i64(self.shape), _lib.u32(self.r), _lib.u32(self.f),
                                            float(sigma), float(h), float(n_eff), _lib.SEMANTICS[semantics], code,
-                                           _lib.KERNELS[kernel]))
+                                           _lib.KERNELS["tiled"], role_arg)
+        if rc != 0:
+            _lib.check(L.ndnlm_plan_create_roles(ctypes.byref(self._h), _lib.i64(self.shape), _lib.u32(self.r),
+                                                 _lib.u32(self.f), float(sigma), float(h), float(n_eff),
+                                                 _lib.SEMANTICS[semantics], code, _lib.KERNELS[kernel], role_arg))
         info = _lib.Info()
         _lib.check(L.ndnlm_plan_info(self._h, ctypes.byref(info)))
         self.info = info
         self.kernel_name = info.kernel_name.decode()
+        self.roles = tuple(int(a) for a in info.role_axis)
         self.is_tiled = info.kernel == _lib.KERNEL_TILED
         self.padded_bytes = int(info.padded_bytes)
         self.out_bytes = int(info.out_bytes)

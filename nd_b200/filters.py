@@ -387,8 +387,15 @@ class NLMeansFilter(Filter):
             if self.n_eff < 0:
                 _out[...] = values
                 return
+        njobs = getattr(self, '_njobs', 1)
+        shard_axis = None
+        shard_dim = getattr(self, '_shard_dim', None)
+        if njobs != 1 and shard_dim in self.dims:
+            # `_parallel_dimension` picked a filtered dimension (there is no other one): its position among the
+            # kernel axes.  A non-filtered dimension is found by the same rule one level down (largest free axis).
+            shard_axis = len(pad_before) + self.dims.index(shard_dim)
         _pixelwise_nlmeans_3d(values, _out, r, f, self.sigma, self.h, self.n_eff,
-                              semantics=self.semantics, kernel=self.kernel, njobs=getattr(self, '_njobs', 1))
+                              semantics=self.semantics, kernel=self.kernel, njobs=njobs, shard_axis=shard_axis)
 
 
 nlmeans = wrap_algorithm(NLMeansFilter, 'nlmeans')

@@ -22,15 +22,18 @@ class ShardPlan:
         n, chunks, halo = int(n), int(chunks), int(halo)
         if chunks < 1:
             raise ValueError('chunks must be >= 1')
-        chunksize = int(math.ceil(n / chunks))
         self.n = n
         self.halo = halo
-        self.ranges = [(i * chunksize, min((i + 1) * chunksize, n)) for i in range(chunks) if i * chunksize < n]
-        if len(self.ranges) > 1:
-            for lo, hi in self.ranges:
-                if hi - lo < halo:
-                    raise ValueError('shard of %d rows is smaller than the halo r+f=%d; use fewer shards'
-                                     % (hi - lo, halo))
+        # Every shard must hold at least halo + 1 rows: its neighbours take `halo` rows from it and a global edge
+        # reflects once (ndnlm_plan_create: r + f <= N - 1).  Where the reference's `xr_split` would hand out
+        # thinner chunks, use fewer shards (njobs larger than the cube can carry degrades, it does not fail).
+        while True:
+            chunksize = int(math.ceil(n / chunks))
+            self.ranges = [(i * chunksize, min((i + 1) * chunksize, n)) for i in range(chunks) if i * chunksize < n]
+            if len(self.ranges) <= 1 or min(hi - lo for lo, hi in self.ranges) >= halo + 1:
+                break
+            chunks = len(self.ranges) - 1
+        self.requested = chunks
 
     @classmethod
     def from_rows(cls, n, rows, halo):

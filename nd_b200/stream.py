@@ -13,6 +13,8 @@ Every slab is copied with its buffer rows, but only its interior is filtered: th
 halo of the staged cube (NDNLM_EDGE_SOURCE), so no voxel is computed twice and the result is bitwise the
 unsliced call (a voxel's arithmetic does not depend on where its slab starts).
 """
+import itertools
+
 import numpy as np
 import torch
 
@@ -114,17 +116,45 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
         idx[k0] = slice(lo, hi)
         return t[tuple(idx)]
 
+    # Host <-> device copies are issued per CONTIGUOUS chunk ([outer index][rows] of the memory-order views: one
+    # chunk for a C-ordered (N0, N1, N2, V) array, V chunks for the variable-major block `Filter.apply` hands
+    # over), so every copy is a plain cudaMemcpyAsync.  Pinned host arrays are copied in place; pageable ones
+    # (NumPy arrays of a Dataset) go through double-buffered pinned staging slabs filled / drained by this thread,
+    # which keeps the DMA asynchronous and overlapped with the kernels.
+    outer = list(itertools.product(*[range(n) for n in in_shape[:k0]])) or [()]
+    pinned_in, pinned_out = hv_in.is_pinned(), hv_out.is_pinned()
+    st_in = None if pinned_in else [torch.empty(in_shape, dtype=tdtype, pin_memory=True) for _ in range(2)]
+    st_out = None if pinned_out else [torch.empty(out_shape, dtype=tdtype, pin_memory=True) for _ in range(2)]
+    ev_st_in_free = [None, None]  # H2D out of staging slab b finished -> it may be refilled
+    pending_out = [None, None]    # (event, lo, hi): staging slab b holds filtered rows still to be copied out
+
+    def drain(b):
+        if pending_out[b] is not None:
+            ev, lo_, hi_ = pending_out[b]
+            ev.synchronize()
+            for ix in outer:
+                hv_out[ix][lo_:hi_].copy_(st_out[b][ix][:hi_ - lo_])
+            pending_out[b] = None
+
     for i in range(sp.nshards):
         b = i & 1
         lo, hi = sp.ranges[i]
         blo, bhi = sp.buffered_range(i)
         rows = bhi - blo
+        if not pinned_in:
+            if ev_st_in_free[b] is not None:
+                ev_st_in_free[b].synchronize()
+            for ix in outer:
+                st_in[b][ix][:rows].copy_(hv_in[ix][blo:bhi])
         with torch.cuda.stream(s_h2d):
             if ev_in_free[b] is not None:
                 s_h2d.wait_event(ev_in_free[b])
-            block(d_in[b], 0, rows).copy_(block(hv_in, blo, bhi), non_blocking=True)
+            for ix in outer:
+                src = hv_in[ix][blo:bhi] if pinned_in else st_in[b][ix][:rows]
+                d_in[b][ix][:rows].copy_(src, non_blocking=True)
             ev_h2d = torch.cuda.Event()
             ev_h2d.record(s_h2d)
+            ev_st_in_free[b] = ev_h2d
         with torch.cuda.stream(s_comp):
             s_comp.wait_event(ev_h2d)
             if ev_out_free[b] is not None:
@@ -141,12 +171,21 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
             ev_comp = torch.cuda.Event()
             ev_comp.record(s_comp)
             ev_in_free[b] = ev_comp
+        if not pinned_out:
+            drain(b)                                                   # staging slab b is about to be overwritten
         with torch.cuda.stream(s_d2h):
             s_d2h.wait_event(ev_comp)
-            block(hv_out, lo, hi).copy_(block(d_out[b], 0, hi - lo), non_blocking=True)
+            for ix in outer:
+                dst = hv_out[ix][lo:hi] if pinned_out else st_out[b][ix][:hi - lo]
+                dst.copy_(d_out[b][ix][:hi - lo], non_blocking=True)
             ev_d2h = torch.cuda.Event()
             ev_d2h.record(s_d2h)
             ev_out_free[b] = ev_d2h
+            if not pinned_out:
+                pending_out[b] = (ev_d2h, lo, hi)
+    if not pinned_out:
+        drain(0)
+        drain(1)
     for s in (s_h2d, s_comp, s_d2h):
         cur.wait_stream(s)
     cur.synchronize()

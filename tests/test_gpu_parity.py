@@ -241,6 +241,44 @@ def test_sharded_equals_unsharded_bitwise(dev, nshards):
     assert np.array_equal(whole, parts)
 
 
+def test_sharded_threaded_host_pipelines_equal_unsharded_bitwise(dev):
+    """njobs > 1 over a host array: one slab pipeline per shard, each in its own thread, reading its neighbours'
+    r+f buffer rows from the host array (two shards on ONE GPU here; two GPUs in test_njobs_two_gpus...)."""
+    from nd_b200._filters import _pixelwise_nlmeans_3d
+    a = sar_like((230, 40, 8, 4), seed=14, dtype=np.float32)
+    r, f = np.array([3, 3, 1], np.uint32), np.array([1, 1, 1], np.uint32)
+    whole = np.empty_like(a)
+    _pixelwise_nlmeans_3d(a, whole, r, f, 0.3, 0.6, pipeline=False)
+    for vmajor in (False, True):
+        b = np.moveaxis(np.ascontiguousarray(np.moveaxis(a, -1, 0)), 0, -1) if vmajor else a
+        parts = np.full_like(b, np.nan)
+        _pixelwise_nlmeans_3d(b, parts, r, f, 0.3, 0.6, devices=[0, 0, 0])
+        assert np.array_equal(whole, parts), vmajor
+        resident = np.full_like(b, np.nan)
+        _pixelwise_nlmeans_3d(b, resident, r, f, 0.3, 0.6, devices=[0, 0, 0], pipeline=False)    # halo rows over peer copies
+        assert np.array_equal(whole, resident), vmajor
+
+
+def test_uneven_shards_along_axis_1_keep_the_roles_of_the_whole_array(dev):
+    """the X / R roles are chosen from the extents of axes 1 and 2, so shards cut along axis 1 whose
+    extent drops below shape[2] used to stage another layout than their neighbours (scrambled halo rows).  Every
+    shard now takes the roles of the whole array (ndnlm_plan_create_roles)."""
+    from nd_b200._filters import _pixelwise_nlmeans_3d
+    a = sar_like((12, 37, 20, 4), seed=15, dtype=np.float32)            # whole: 37 > 20; shards of 19 / 18 < 20
+    r, f = np.array([1, 2, 2], np.uint32), np.array([1, 1, 1], np.uint32)
+    whole = np.empty_like(a)
+    _pixelwise_nlmeans_3d(a, whole, r, f, 0.3, 0.6)
+    parts = np.full_like(a, np.nan)
+    _pixelwise_nlmeans_3d(a, parts, r, f, 0.3, 0.6, devices=[0, 0], shard_axis=1)
+    assert scaled_err(parts, whole) < 1e-6
+    p_whole = dev.Plan(a.shape, r, f, 0.3, 0.6)
+    p_shard = dev.Plan((12, 19, 20, 4), r, f, 0.3, 0.6)
+    assert p_whole.roles != p_shard.roles                                 # the situation the fix is for
+    assert dev.Plan((12, 19, 20, 4), r, f, 0.3, 0.6, roles=p_whole.roles).roles == p_whole.roles
+    with pytest.raises(ValueError):
+        dev.Plan(a.shape, r, f, 0.3, 0.6, roles=(0, 0, 1))
+
+
 def test_large_cube_sampled_against_oracle(dev, c_oracle):
     """cfg3 parameters on a cube that is many tiles in every direction; sub-cubes (corner, edge, interior)
     are checked against the oracle run on the same values (with halo r+f around the sample)."""
@@ -351,3 +389,87 @@ def test_njobs_two_gpus_equals_one_gpu(dev):
         two = NLMeansFilter(dims=dims, r=2, sigma=1, h=1).apply(ds, njobs=2)
         for v in ds.data_vars:
             assert np.array_equal(one[v].values, two[v].values), (dims, v)
+
+
+def _nccl_rank(rank, world, port, shape, r, f, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from nd_b200 import device
+        from nd_b200.shard import DistributedShard, ShardPlan
+        a = sar_like(shape, seed=31, dtype=np.float32)                  # every rank derives the same global cube
+        sp = ShardPlan(shape[0], world, r[0] + f[0])
+        lo, hi = sp.ranges[rank]
+        slab = torch.from_numpy(np.ascontiguousarray(a[lo:hi])).cuda()
+        plan = device.Plan(slab.shape, r, f, 0.3, 0.6)
+        shard = DistributedShard(plan, axis=0, rank=rank, world=world)
+        out = torch.empty_like(slab)
+        shard.stage(slab)
+        nmsg = shard.exchange()
+        shard.run()
+        shard.unstage(out)
+        torch.cuda.synchronize()
+        q.put((rank, lo, hi, nmsg, out.cpu().numpy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_nccl_ranks_seam_rows_match_the_oracle(dev, c_oracle):
+    """One process per GPU, halo rows over NCCL send/recv (the path bench.py scales on): every rank's rows -- the
+    seam rows in particular -- against the oracle run on the whole cube, and bitwise against the unsharded GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    shape, r, f = (44, 40, 9, 4), (3, 3, 1), (1, 1, 1)
+    a = sar_like(shape, seed=31, dtype=np.float32)
+    ref = c_oracle.nlmeans(a, r, f, 0.3, 0.6, threads=8)
+    whole, _ = run_plan(dev, a, r, f, 0.3, 0.6)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_rank, args=(k, 2, port, shape, r, f, q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, lo, hi, nmsg, out in got:
+        assert nmsg == 2                                                 # one send + one recv per interior edge
+        assert np.array_equal(out, whole[lo:hi]), rank
+        assert scaled_err(out, ref[lo:hi]) < TOL32
+        seam = slice(hi - 4, hi) if rank == 0 else slice(lo, lo + 4)
+        assert scaled_err(out[seam.start - lo:seam.stop - lo], ref[seam]) < TOL32
+
+
+def test_apply_on_a_real_xarray_dataset(dev):
+    """north_star: `NLMeansFilter(...).apply(ds)` takes and returns an xarray.Dataset with the same dims, coords and
+    attrs (reference nd/filters.py:105-191).  xarray is absent from this image; the test runs wherever it exists."""
+    xr = pytest.importorskip("xarray")
+    from nd_b200.filters import NLMeansFilter
+    rng = np.random.default_rng(3)
+    coords = {"y": np.linspace(50.0, 51.0, 24), "x": np.linspace(10.0, 11.0, 30), "time": np.arange(6)}
+    ds = xr.Dataset({"C11": (("y", "x", "time"), rng.gamma(4.0, 0.25, (24, 30, 6))),
+                     "C22": (("y", "x", "time"), rng.gamma(4.0, 0.25, (24, 30, 6))),
+                     "C12": (("y", "x", "time"), rng.normal(size=(24, 30, 6)) + 1j * rng.normal(size=(24, 30, 6))),
+                     "mask": (("y", "x"), np.ones((24, 30)))}, coords=coords, attrs={"crs": "EPSG:4326"})
+    out = NLMeansFilter(dims=("y", "x", "time"), r=(2, 2, 1), sigma=0.3, h=0.6).apply(ds)
+    assert isinstance(out, xr.Dataset) and dict(out.attrs) == dict(ds.attrs)
+    assert set(out.data_vars) == set(ds.data_vars) and out["C11"].dims == ds["C11"].dims
+    for c in coords:
+        assert np.array_equal(out[c].values, ds[c].values)
+    assert np.iscomplexobj(out["C12"].values) and np.array_equal(out["mask"].values, ds["mask"].values)
+    assert out["C11"].values.std() < ds["C11"].values.std()
+    t_first = NLMeansFilter(dims=("time", "y", "x"), r=(1, 2, 2), sigma=0.3, h=0.6).apply(ds.transpose("time", "y", "x"))
+    np.testing.assert_allclose(t_first["C11"].transpose("y", "x", "time").values, out["C11"].values, rtol=1e-5, atol=1e-7)
+

@@ -193,9 +193,22 @@ def test_shard_plan_matches_xr_split(n, chunks, halo):
         assert sp.edges(i) == ('reflect' if i == 0 else 'halo', 'reflect' if i == sp.nshards - 1 else 'halo')
 
 
-def test_shard_plan_rejects_shards_smaller_than_halo():
-    with pytest.raises(ValueError):
-        ShardPlan(16, 8, 6)
+@pytest.mark.parametrize("n,chunks,halo,expect", [(16, 8, 6, 2), (13, 8, 6, 1), (40, 8, 4, 8), (39, 8, 4, 5), (7, 3, 6, 1)])
+def test_shard_plan_degrades_to_fewer_shards_when_they_cannot_carry_the_halo(n, chunks, halo, expect):
+    """njobs larger than the cube can carry: fewer shards, like `xr_split` handing out fewer chunks, never an
+    opaque radius error later (every shard keeps halo + 1 rows: `halo` for its neighbour, one to reflect about)."""
+    sp = ShardPlan(n, chunks, halo)
+    assert sp.nshards == expect
+    assert sp.ranges[0][0] == 0 and sp.ranges[-1][1] == n
+    assert sp.nshards == 1 or all(hi - lo >= halo + 1 for lo, hi in sp.ranges)
+
+
+def test_choose_shard_axis():
+    from nd_b200._filters import choose_shard_axis
+    assert choose_shard_axis((1, 300, 200, 4), (0, 3, 3), (0, 1, 1), 4) == 1       # 2-D: the free axis has one row
+    assert choose_shard_axis((24, 300, 200, 4), (0, 3, 3), (0, 1, 1), 4) == 0      # a real free axis (time first)
+    assert choose_shard_axis((4, 300, 200, 4), (0, 3, 3), (0, 1, 1), 8) == 1       # free axis shorter than njobs
+    assert choose_shard_axis((100, 300, 20, 4), (2, 2, 1), (1, 1, 1), 2) == 1      # all filtered: the largest
 
 
 @pytest.mark.parametrize("n,rows,halo", [(4096, 126, 6), (4108, 126, 6), (100, 48, 4), (200, 64, 0), (130, 64, 6), (50, 100, 3),
