@@ -325,9 +325,12 @@ def check_parity(wl, samples, gpu_blocks, get_rows, global_rows, semantics):
         for v in range(V):
             scale = max(float(np.abs(ref[..., v]).max()), 1e-30)
             err = max(err, float(np.abs(got[..., v].astype(np.float64) - ref[..., v]).max()) / scale)
-        if not np.isfinite(got).all():
+        if not (np.isfinite(got).all() and np.isfinite(ref).all()):
             err = float("inf")
-        rep.append({"name": smp["name"], "y": list(smp["y"]), "x": list(smp["x"]), "t": list(smp["t"]), "err": err})
+        rep.append({"name": smp["name"], "y": list(smp["y"]), "x": list(smp["x"]), "t": list(smp["t"]), "err": err,
+                    "bitwise_equal_values": int((got == ref).sum()), "values": int(ref.size),
+                    "ref_absmax": float(np.abs(ref).max()), "ref_minus_input_absmax":
+                    float(np.abs(ref - crop[y0 - ya:y1 - ya, x0 - xa:x1 - xa, t0 - ta:t1 - ta]).max())})
         worst = max(worst, err)
     return {"max_scaled_err": worst, "tolerance": PARITY_TOL, "ok": bool(worst <= PARITY_TOL), "samples": rep,
             "metric": "max_p |out - ref| / max_p |ref_v| per variable over each sub-cube (SURVEY.md 8(d))",

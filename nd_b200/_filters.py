@@ -97,6 +97,68 @@ def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=No
     _copy_back(output, d_out)
 
 
+def nlmeans_variables(arrays, outputs, r, f, sigma, h, n_eff=-1, *, semantics=None, kernel='auto', njobs=1,
+                      devices=None):
+    """The same filter on V SEPARATE host arrays (one (N0, N1, N2) C-ordered array per variable, as a Dataset holds
+    them) written into V separate outputs -- what `Filter.apply` would otherwise gather into one
+    (N0, N1, N2, V) block, filter, and scatter again (reference nd/filters.py:164-185: `to_array`, deep copy,
+    `xr.merge`): three host-side passes over the data that cost more than the filter once it runs on a GPU.
+    The arrays are streamed straight from / to the Dataset's own memory by the slab pipeline (nd_b200/stream.py),
+    over `njobs` GPUs when asked.  Returns False (nothing done) when the arrays do not qualify for streaming."""
+    import threading
+    import torch
+    from . import stream as _stream
+    from .shard import ShardPlan
+
+    r3 = _as_u32_3(r, 'r')
+    f3 = _as_u32_3(f, 'f')
+    arrays, outputs = list(arrays), list(outputs)
+    if not arrays or any(not isinstance(a, np.ndarray) for a in arrays + outputs):
+        return False
+    a0 = arrays[0]
+    halo = r3[0] + f3[0]
+    ok = (a0.dtype in (np.float32, np.float64) and a0.ndim == 3 and a0.size > 0 and a0.shape[0] >= max(8 * halo, 2)
+          and all(a.shape == a0.shape and a.dtype == a0.dtype and a.flags['C_CONTIGUOUS'] for a in arrays)
+          and all(o.shape == a0.shape and o.dtype == a0.dtype and o.flags['C_CONTIGUOUS'] and o.flags['WRITEABLE']
+                  for o in outputs) and len(outputs) == len(arrays))
+    if not ok:
+        return False
+    _lib.lib()
+    if not torch.cuda.is_available():
+        raise RuntimeError('nd_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    njobs = int(njobs)
+    if njobs == -1:
+        njobs = torch.cuda.device_count()
+    if devices is None:
+        if njobs > torch.cuda.device_count():
+            raise ValueError('njobs=%d but only %d CUDA devices are visible' % (njobs, torch.cuda.device_count()))
+        devices = list(range(njobs)) if njobs > 1 else [torch.cuda.current_device()]
+    sp = ShardPlan(a0.shape[0], len(devices), halo)
+    if sp.nshards > 1 and min(hi - lo for lo, hi in sp.ranges) < 8 * max(halo, 1):
+        sp = ShardPlan(a0.shape[0], 1, halo)
+    errors = []
+
+    def worker(i):
+        try:
+            torch.cuda.set_device(int(devices[i]))
+            _stream.apply_host_pipelined(arrays, outputs, r3, f3, sigma, h, n_eff, semantics=semantics, kernel=kernel,
+                                         row_range=sp.ranges[i])
+        except BaseException as e:
+            errors.append(e)
+
+    if sp.nshards == 1:
+        worker(0)
+    else:
+        threads = [threading.Thread(target=worker, args=(i,)) for i in range(sp.nshards)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    return True
+
+
 def _copy_back(output, d_out):
     import torch
     if all(s >= 0 for s in output.strides) and output.flags.writeable:

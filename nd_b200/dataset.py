@@ -32,7 +32,9 @@ class Variable:
     def sizes(self):
         return OrderedDict(zip(self.dims, self.values.shape))
 
-    def copy(self, deep=True):
+    def copy(self, deep=True, data=None):
+        if data is not None:                       # xarray's `copy(data=...)`: same dims, new values
+            return Variable(self.dims, data)
         return Variable(self.dims, self.values.copy() if deep else self.values)
 
 

@@ -19,7 +19,7 @@ from abc import abstractmethod
 import numpy as np
 
 from .algorithm import Algorithm, parallelize, wrap_algorithm
-from ._filters import _pixelwise_nlmeans_3d
+from ._filters import _pixelwise_nlmeans_3d, nlmeans_variables
 from . import _ndimage as snf          # GPU stand-in for `scipy.ndimage.filters` (same call signatures)
 
 
@@ -154,17 +154,54 @@ class Filter(Algorithm):
             self._filter(ds.values, axes, output=result.values)
         else:
             variables = get_vars_for_dims(ds, self.dims)
-            result = ds.copy(deep=True)
-            if self.per_variable:
+            result = None
+            if not self.per_variable and variables:
+                result = self._apply_joint_streamed(ds, variables)
+            if result is not None:
+                pass
+            elif self.per_variable:
+                result = ds.copy(deep=True)
                 for v in variables:
                     vdims = result[v].dims
                     axes = tuple(list(vdims).index(d) for d in self.dims)
                     self._filter(ds[v].values, axes, output=result[v].values)
-            elif variables:
-                self._apply_joint(ds, result, variables)
+            else:
+                result = ds.copy(deep=True)
+                if variables:
+                    self._apply_joint(ds, result, variables)
 
         if convert_complex:
             assemble_complex(ds)
+        return result
+
+    def _apply_joint_streamed(self, ds, variables):
+        """per_variable=False without the gather / scatter of `_apply_joint`: when every filtered variable already
+        has the layout the kernel wants (dims == filter dims followed by the others, C order, one float dtype) and
+        the filter can take the variables one array each (`_filter_variables`), they are streamed to the GPU straight
+        from the Dataset's own arrays and the result is written straight into the new Dataset's arrays -- no
+        `to_array()` block, no deep copy of what is about to be overwritten, no `xr.merge` (nd/filters.py:164-185).
+        Returns the result Dataset, or None when the fast path does not apply (then `_apply_joint` runs)."""
+        fv = getattr(self, '_filter_variables', None)
+        if fv is None:
+            return None
+        vdims = tuple(ds[variables[0]].dims)
+        ordered_dims = tuple(self.dims) + tuple(d for d in vdims if d not in self.dims)
+        srcs = [ds[v].values for v in variables]
+        if (vdims != ordered_dims or any(tuple(ds[v].dims) != vdims for v in variables)
+                or any(not isinstance(a, np.ndarray) or a.dtype != srcs[0].dtype or a.shape != srcs[0].shape
+                       or not a.flags['C_CONTIGUOUS'] for a in srcs)
+                or srcs[0].dtype not in (np.float32, np.float64)):
+            return None
+        outs = [np.empty_like(a) for a in srcs]
+        axes = tuple(ordered_dims.index(d) for d in self.dims)
+        if not fv(srcs, axes, outs):
+            return None
+        result = ds.copy(deep=False)
+        for v in list(ds.data_vars):
+            if v in variables:
+                result[v] = ds[v].copy(deep=False, data=outs[variables.index(v)])
+            else:
+                result[v] = ds[v].copy(deep=True)
         return result
 
     def _apply_joint(self, ds, result, variables):
@@ -387,15 +424,40 @@ class NLMeansFilter(Filter):
             if self.n_eff < 0:
                 _out[...] = values
                 return
+        njobs, shard_axis = self._njobs_and_shard_axis(len(pad_before))
+        _pixelwise_nlmeans_3d(values, _out, r, f, self.sigma, self.h, self.n_eff,
+                              semantics=self.semantics, kernel=self.kernel, njobs=njobs, shard_axis=shard_axis)
+
+    def _njobs_and_shard_axis(self, leading):
         njobs = getattr(self, '_njobs', 1)
         shard_axis = None
         shard_dim = getattr(self, '_shard_dim', None)
         if njobs != 1 and shard_dim in self.dims:
             # `_parallel_dimension` picked a filtered dimension (there is no other one): its position among the
             # kernel axes.  A non-filtered dimension is found by the same rule one level down (largest free axis).
-            shard_axis = len(pad_before) + self.dims.index(shard_dim)
-        _pixelwise_nlmeans_3d(values, _out, r, f, self.sigma, self.h, self.n_eff,
-                              semantics=self.semantics, kernel=self.kernel, njobs=njobs, shard_axis=shard_axis)
+            shard_axis = leading + self.dims.index(shard_dim)
+        return njobs, shard_axis
+
+    def _filter_variables(self, arrays, axes, outputs):
+        """`_filter` for V separate per-variable arrays (same shape / dtype, C order, dims == filter dims followed by
+        the non-filter dims).  Returns False when this layout cannot be streamed (the caller then gathers the
+        variables into one block and calls `_filter`)."""
+        ndim = arrays[0].ndim
+        if ndim > 3 or ndim < len(self.r) or not np.any(self.r) or len(self.r) == 0:
+            return False
+        pad_before = np.zeros(3 - ndim, dtype=self.r.dtype)
+        pad_after = np.zeros(ndim - len(self.r), dtype=self.r.dtype)
+        r = np.concatenate([pad_before, self.r, pad_after])
+        f = np.concatenate([pad_before, self.f, pad_after])
+        njobs, shard_axis = self._njobs_and_shard_axis(len(pad_before))
+        if shard_axis not in (None, 0):
+            return False
+        a3 = [a.reshape((1,) * (3 - ndim) + a.shape) for a in arrays]
+        o3 = [o.reshape((1,) * (3 - ndim) + o.shape) for o in outputs]
+        if r[0] == 0 and f[0] == 0 and njobs > 1 and a3[0].shape[0] < njobs:
+            return False                      # a short free leading axis: shard along a filtered one (block path)
+        return nlmeans_variables(a3, o3, r, f, self.sigma, self.h, self.n_eff, semantics=self.semantics,
+                                 kernel=self.kernel, njobs=njobs)
 
 
 nlmeans = wrap_algorithm(NLMeansFilter, 'nlmeans')

@@ -14,12 +14,59 @@ halo of the staged cube (NDNLM_EDGE_SOURCE), so no voxel is computed twice and t
 unsliced call (a voxel's arithmetic does not depend on where its slab starts).
 """
 import itertools
+import math
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
 
 from . import device as dev
 from .shard import ShardPlan
+
+
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(16, os.cpu_count() or 2)), thread_name_prefix='ndb200-copy')
+    return _POOL
+
+
+def par_copy(dst, src):
+    """dst.copy_(src) for two equally shaped CPU tensors, split over a few threads when it is large: one thread
+    moves ~5 GB/s between pageable and pinned memory, far below what PCIe and the kernels sustain."""
+    nbytes = src.numel() * src.element_size()
+    if nbytes < (64 << 20) or src.dim() == 0 or src.shape[0] < 2:
+        dst.copy_(src)
+        return
+    parts = int(min(_pool()._max_workers, max(1, nbytes // (32 << 20)), src.shape[0]))
+    step = int(math.ceil(src.shape[0] / parts))
+    futs = [_pool().submit(dst[a:a + step].copy_, src[a:a + step]) for a in range(0, src.shape[0], step)]
+    for f in futs:
+        f.result()
+
+
+class _Shape:
+    """shape / dtype / itemsize of the logical (N0, N1, N2, V) array when the variables are separate arrays."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype, self.itemsize, self.ndim = shape, np.dtype(dtype), np.dtype(dtype).itemsize, 4
+
+
+class _VarList:
+    """V separate (N0, N1, N2) host arrays seen as the chunks [v] of a variable-major block."""
+
+    def __init__(self, arrays):
+        self.t = [torch.from_numpy(a) for a in arrays]
+
+    def __getitem__(self, ix):
+        return self.t[ix[0]]
+
+    def is_pinned(self):
+        return all(t.is_pinned() for t in self.t)
 
 
 def dense_axis_order(a):
@@ -46,13 +93,29 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
     """Filter host array `arr` into host array `output` through the slab pipeline.  Raises
     ValueError('No solution') like the reference when find_weight fails anywhere.
 
+    `arr` / `output` may also be two LISTS of V dense C-ordered (N0, N1, N2) arrays, one per variable (what a Dataset
+    holds): they are streamed as the chunks of a variable-major block without ever being gathered into one on the host.
     row_range=(lo, hi) restricts the work to rows [lo, hi) of axis 0 (the rows outside are still read as the
     buffer of the first / last slab): one GPU's share of a multi-GPU apply over a host array.
     copy_only=True runs the same slabs, streams and copies WITHOUT the kernels (the filtered rows are a device
     copy of the input): the host-memory / PCIe ceiling of this pipeline, reported by bench.py beside `e2e`."""
-    order = dense_axis_order(arr)
-    if order is None or order != dense_axis_order(output):
-        raise ValueError('apply_host_pipelined needs dense arrays with identical memory layout')
+    per_variable = isinstance(arr, (list, tuple))
+    if per_variable:
+        if len(arr) != len(output) or not arr:
+            raise ValueError('need one output array per input variable')
+        for a, o in zip(arr, output):
+            if (a.ndim != 3 or a.shape != arr[0].shape or o.shape != a.shape or a.dtype != arr[0].dtype or o.dtype != a.dtype
+                    or not (a.flags['C_CONTIGUOUS'] and o.flags['C_CONTIGUOUS'])):
+                raise ValueError('per-variable arrays must be C-contiguous (N0, N1, N2) arrays of one shape and dtype')
+        order = [3, 0, 1, 2]
+        hv_in, hv_out = _VarList(arr), _VarList(output)
+        arr = _Shape(tuple(arr[0].shape) + (len(arr),), arr[0].dtype)
+    else:
+        order = dense_axis_order(arr)
+        if order is None or order != dense_axis_order(output):
+            raise ValueError('apply_host_pipelined needs dense arrays with identical memory layout')
+        hv_in = torch.from_numpy(arr.transpose(order))
+        hv_out = torch.from_numpy(output.transpose(order))
     n0 = arr.shape[0]
     halo = int(r3[0]) + int(f3[0])
     device = torch.device('cuda', torch.cuda.current_device())
@@ -77,8 +140,6 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
 
     # host views in memory order: hv[outer..., rows, inner...] with every [outer][lo:hi] block contiguous
     k0 = order.index(0)
-    hv_in = torch.from_numpy(arr.transpose(order))
-    hv_out = torch.from_numpy(output.transpose(order))
     inv = [order.index(a) for a in range(4)]
     max_buf = max(sp.buffered_range(i)[1] - sp.buffered_range(i)[0] for i in range(sp.nshards))
     max_int = max(hi - lo for lo, hi in sp.ranges)
@@ -133,7 +194,7 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
             ev, lo_, hi_ = pending_out[b]
             ev.synchronize()
             for ix in outer:
-                hv_out[ix][lo_:hi_].copy_(st_out[b][ix][:hi_ - lo_])
+                par_copy(hv_out[ix][lo_:hi_], st_out[b][ix][:hi_ - lo_])
             pending_out[b] = None
 
     for i in range(sp.nshards):
@@ -145,7 +206,7 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
             if ev_st_in_free[b] is not None:
                 ev_st_in_free[b].synchronize()
             for ix in outer:
-                st_in[b][ix][:rows].copy_(hv_in[ix][blo:bhi])
+                par_copy(st_in[b][ix][:rows], hv_in[ix][blo:bhi])
         with torch.cuda.stream(s_h2d):
             if ev_in_free[b] is not None:
                 s_h2d.wait_event(ev_in_free[b])
