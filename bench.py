@@ -687,7 +687,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "f32", "data": data_kind, "config": config,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "parity": parity,
-            "cpu_baseline": cpu, "no_solution_flag": flag}
+            "cpu_baseline": cpu, "kernel_flag": flag}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:

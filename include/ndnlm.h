@@ -39,6 +39,8 @@ extern "C" {
 #define NDNLM_EDTYPE         -2   /* non float32/float64 data -> TypeError (ref: "No matching signature") */
 #define NDNLM_ECUDA          -3   /* CUDA runtime / driver failure -> RuntimeError                 */
 #define NDNLM_ENOSOLUTION    -4   /* find_weight: ValueError('No solution') (ref nd/_filters.pyx:310-311) */
+#define NDNLM_WUNDERFLOW      1   /* WARNING (result valid): some voxels saw only weights below the fp32 range and were
+                                     left unfiltered -> RuntimeWarning (the float64 reference keeps such weights)        */
 #define NDNLM_ERADIUS        -5   /* r_i + f_i > N_i - 1: single reflection undefined (ref `_idx` :34-40 is UB) */
 
 /* ---- dtypes of the caller's arrays ---- */
@@ -50,10 +52,12 @@ extern "C" {
 #define NDNLM_REFERENCE_COMPILED  1  /* bug-for-bug the LP64 binary: any f_i>0 => d^2 == 0 (nd/_filters.pyx:323,373-375) */
 
 /* ---- kernel selection ---- */
-#define NDNLM_KERNEL_AUTO     0  /* tiled fp32 kernel when the configuration has an instantiation, else generic */
+#define NDNLM_KERNEL_AUTO     0  /* tiled kernel in the data type when the configuration has an instantiation, else generic */
 #define NDNLM_KERNEL_GENERIC  1  /* reference-faithful one-thread-per-voxel kernel (fp64 weights), any r/f/V      */
 #define NDNLM_KERNEL_TILED    2  /* TMA-tiled fp32 kernel; error if not instantiated for this configuration.      */
                                  /* With float64 data: staged as float32, result widened back (opt-in fp32 compute) */
+#define NDNLM_KERNEL_TILED_F64 3 /* float64 data on the float64 instantiations of the tiled kernel (what AUTO picks */
+                                 /* for float64 data when one fits); error if there is none                         */
 
 /* ---- how the two ends of user axis `shard_axis` are padded by ndnlm_stage ---- */
 #define NDNLM_EDGE_REFLECT 0     /* global edge: reflect locally (reference `_idx`, nd/_filters.pyx:34-40) */
@@ -139,9 +143,13 @@ int ndnlm_halo_unpack(const ndnlm_plan_t* plan, void* padded, int axis, int side
 /*
  * Run the filter: padded cube -> internal output buffer (`out_internal`, info.out_bytes).
  * Replaces the voxel / search-window / patch loops of nd/_filters.pyx:351-420.
- * `err_flag` is a device int32 (zeroed by the caller); the kernels set it to 1 when find_weight
- * has no solution (nd/_filters.pyx:310-311); the caller turns that into ValueError('No solution').
+ * `err_flag` is a device int32 (zeroed by the caller), a bit mask the kernels OR into:
+ *   NDNLM_FLAG_NOSOLUTION  find_weight has no solution at some voxel (nd/_filters.pyx:310-311) -> ValueError('No solution')
+ *   NDNLM_FLAG_UNDERFLOW   fp32 tiled kernel only: at some voxel every neighbour weight flushed to zero (< 2^-126);
+ *                          that voxel is returned unfiltered -> a warning, never a silent NaN
  */
+#define NDNLM_FLAG_NOSOLUTION 1
+#define NDNLM_FLAG_UNDERFLOW  2
 int ndnlm_run(const ndnlm_plan_t* plan, const void* padded, void* out_internal,
               int32_t* err_flag, void* stream);
 
@@ -159,7 +167,7 @@ int ndnlm_unstage(const ndnlm_plan_t* plan, const void* out_internal,
 
 /*
  * One-call form of the reference entry point on device arrays: stage + run + unstage on `stream`,
- * then synchronises the stream and returns NDNLM_ENOSOLUTION if the error flag was raised.
+ * then synchronises the stream and returns NDNLM_ENOSOLUTION / NDNLM_WUNDERFLOW according to the flag.
  * `workspace` must hold ndnlm_workspace_bytes(plan) bytes.
  */
 size_t ndnlm_workspace_bytes(const ndnlm_plan_t* plan);

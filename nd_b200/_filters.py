@@ -254,10 +254,9 @@ def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, sha
             d_out = torch.empty_like(slabs[i][1])
             plan.unstage(internal, d_out)
         outs.append(d_out); flags.append(flag)
-    bad = False
+    bad = 0
     for i, d_out in enumerate(outs):
         torch.cuda.synchronize(devices[i])
-        bad = bad or bool(flags[i].item())
+        bad |= int(flags[i].item())
         output[tuple(slabs[i][0])] = d_out.cpu().numpy()
-    if bad:
-        raise ValueError('No solution')
+    _lib.check_flag(bad)

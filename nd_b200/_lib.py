@@ -12,13 +12,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NDNLM_LIB") or os.path.join(_HERE, "libndnlm.so")   # NDNLM_LIB: tuning builds only
 
 OK, EINVAL, EDTYPE, ECUDA, ENOSOLUTION, ERADIUS = 0, -1, -2, -3, -4, -5
+WUNDERFLOW = 1
+FLAG_NOSOLUTION, FLAG_UNDERFLOW = 1, 2
 F32, F64 = 0, 1
 AS_WRITTEN, REFERENCE_COMPILED = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED = 0, 1, 2
 EDGE_REFLECT, EDGE_HALO, EDGE_SOURCE = 0, 1, 2
 
 SEMANTICS = {"as_written": AS_WRITTEN, "reference_compiled": REFERENCE_COMPILED}
-KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "tiled": KERNEL_TILED}
+KERNEL_TILED_F64 = 3
+KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "tiled": KERNEL_TILED, "tiled64": KERNEL_TILED_F64}
 
 # every symbol include/ndnlm.h declares (tests check that the library exports all of them)
 SYMBOLS = [
@@ -137,6 +140,10 @@ def check(rc):
     if rc == OK:
         return
     msg = lib().ndnlm_last_error().decode("utf-8", "replace")
+    if rc == WUNDERFLOW:
+        import warnings
+        warnings.warn("ndnlm: " + msg, RuntimeWarning, stacklevel=3)
+        return
     if rc == EDTYPE:
         raise TypeError(msg)                      # reference: "No matching signature found"
     if rc == ENOSOLUTION:
@@ -144,6 +151,17 @@ def check(rc):
     if rc in (EINVAL, ERADIUS):
         raise ValueError(msg)
     raise RuntimeError("ndnlm: " + msg)
+
+
+def check_flag(value):
+    """The device error flag of ndnlm_run (a bit mask) -> the reference's exception / a warning."""
+    value = int(value)
+    if value & FLAG_NOSOLUTION:
+        raise ValueError("No solution")           # reference nd/_filters.pyx:310-311
+    if value & FLAG_UNDERFLOW:
+        import warnings
+        warnings.warn("ndnlm: at some voxels every neighbour weight is below the float32 range (< 2^-126); they were "
+                      "left unfiltered (use float64 data or a larger h)", RuntimeWarning, stacklevel=3)
 
 
 def i64(values):

@@ -165,9 +165,12 @@ def gaussian_plan(ndim, sigma, order=0, mode='reflect', truncate=4.0, radius=Non
     return plan
 
 
-def gaussian_filter_device(t_in, t_out, sigma, order=0, mode='reflect', cval=0.0, truncate=4.0, radius=None, axes=None):
+def gaussian_filter_device(t_in, t_out, sigma, order=0, mode='reflect', cval=0.0, truncate=4.0, radius=None, axes=None,
+                           integer=False):
     """Sequence of 1-D correlations like scipy: every pass rounds to the array dtype; pass k reads the output
-    of pass k-1.  Needs one scratch tensor because the kernels are out of place."""
+    of pass k-1.  Needs one scratch tensor because the kernels are out of place.  `integer`: the caller's array
+    has an integer dtype and is carried as float64 here -- scipy stores every pass into the integer output with a
+    C cast, i.e. truncation toward zero, which is applied between the passes."""
     _check_pair(t_in, t_out)
     plan = gaussian_plan(t_in.dim(), sigma, order, mode, truncate, radius, axes)
     if not plan:
@@ -179,28 +182,43 @@ def gaussian_filter_device(t_in, t_out, sigma, order=0, mode='reflect', cval=0.0
         # the last pass must land in t_out; alternate between t_out and the scratch tensor before it
         dst = t_out if (len(plan) - 1 - k) % 2 == 0 else scratch
         correlate1d_device(src, dst, weights, axis, 0, md, cval)
+        if integer:
+            dst.trunc_()
         src = dst
     return t_out
 
 
 # ---- host level (scipy.ndimage signatures) -------------------------------------------------------------
+def _is_integer(a):
+    return np.issubdtype(np.asarray(a).dtype, np.integer)
+
+
 def _to_device(a):
+    """float32 / float64 arrays go to the device as they are.  Integer rasters (uint8 / int16 ... as scipy accepts
+    them, nd/filters.py:260-268) are carried as float64 -- scipy computes every output value in double and stores
+    it into an array of the input dtype with a C cast (`_finish` does the same)."""
     a = np.asarray(a)
+    if _is_integer(a):
+        a = a.astype(np.float64)
     if a.dtype not in (np.float32, np.float64):
-        raise TypeError('nd_b200 filters support float32 / float64 data only (got %s)' % a.dtype)
+        raise TypeError('nd_b200 filters support float32 / float64 and integer data only (got %s)' % a.dtype)
     if not torch.cuda.is_available():
         raise RuntimeError('nd_b200 filters need a CUDA device; there is no CPU fallback')
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
 def _finish(result, input, output):
+    res = result.cpu().numpy()
+    if _is_integer(input):
+        with np.errstate(invalid='ignore'):
+            res = np.trunc(res).astype(np.asarray(input).dtype)      # the C cast of scipy's output store
     if output is None:
-        return result.cpu().numpy()
+        return res
     if not isinstance(output, np.ndarray):
         raise TypeError('output must be a numpy array (or None)')
     if output.shape != np.asarray(input).shape:
         raise RuntimeError('output shape not correct')
-    output[...] = result.cpu().numpy()
+    output[...] = res
     return output
 
 
@@ -261,7 +279,7 @@ def gaussian_filter1d(input, sigma, axis=-1, order=0, output=None, mode='reflect
     input = np.asarray(input)
     t_in = _to_device(input)
     t_out = torch.empty_like(t_in)
-    gaussian_filter_device(t_in, t_out, sigma, order, mode, cval, truncate, radius, axes=axis)
+    gaussian_filter_device(t_in, t_out, sigma, order, mode, cval, truncate, radius, axes=axis, integer=_is_integer(input))
     return _finish(t_out, input, output)
 
 
@@ -272,5 +290,5 @@ def gaussian_filter(input, sigma, order=0, output=None, mode='reflect', cval=0.0
         raise TypeError('Complex type not supported')
     t_in = _to_device(input)
     t_out = torch.empty_like(t_in)
-    gaussian_filter_device(t_in, t_out, sigma, order, mode, cval, truncate, radius, axes)
+    gaussian_filter_device(t_in, t_out, sigma, order, mode, cval, truncate, radius, axes, integer=_is_integer(input))
     return _finish(t_out, input, output)

@@ -40,6 +40,10 @@ def parallelize(func):
             return method(ds, *args, **kwargs)
         # The shard layer lives below the Dataset marshalling: the filter sees `_njobs`
         # and splits the staged cube over that many GPUs (nd_b200/shard.py).
+        if not getattr(self, '_supports_njobs', False):
+            import warnings
+            warnings.warn('%s has no multi-GPU shard layer: njobs=%d runs on one GPU with the same result (these '
+                          'filters are HBM-bound, milliseconds per GB)' % (type(self).__name__, njobs))
         prev = getattr(self, '_njobs', 1)
         self._njobs = int(njobs)
         self._shard_dim = self._parallel_dimension(ds)

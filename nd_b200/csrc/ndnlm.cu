@@ -72,6 +72,7 @@ static inline unsigned blocks_for(long long total, int threads) { return unsigne
 #include "nlm_tiled_launch.cuh"
 
 struct TiledInst {
+    int elem;           // bytes per element of the staged cube the kernel computes in: 4 (float) or 8 (double)
     int nv4, fw, fx, fr, L, nwarps, ch;
     bool neff;
     size_t exch_bytes;
@@ -81,20 +82,31 @@ struct TiledInst {
 
 // The instantiations live in ndnlm_tiled_g*.cu (explicit instantiation definitions); here they are only declared.
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                        \
-    extern template cudaError_t launch_tiled<NV4, FW, FX, FR, L, NW, CH, NEFF>(                               \
-        const CUtensorMap&, const ndnlm::DevParams&, const float4*, float4*, int*, int, size_t, cudaStream_t);
+    extern template cudaError_t launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF>(                        \
+        const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
+#define TILED_INST64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                      \
+    extern template cudaError_t launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF>(                       \
+        const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
 #include "instances_g0.inc"
 #include "instances_g1.inc"
 #include "instances_g2.inc"
 #include "instances_g3.inc"
 #include "instances_g4.inc"
+#include "instances_g5.inc"
 #undef TILED_INST
+#undef TILED_INST64
 
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
     {                                                                                                \
-        NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES,     \
-            launch_tiled<NV4, FW, FX, FR, L, NW, CH, NEFF>,                                          \
+        4, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+            launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF>,                                   \
             "nlm_tiled<nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
+    },
+#define TILED_INST64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                               \
+    {                                                                                                \
+        8, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<double, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+            launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF>,                                  \
+            "nlm_tiled<double,nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
     },
 
 // Candidates are tried in order; the first whose shared-memory box fits is used.
@@ -104,8 +116,10 @@ static const TiledInst g_tiled[] = {
 #include "instances_g2.inc"
 #include "instances_g3.inc"
 #include "instances_g4.inc"
+#include "instances_g5.inc"
 };
 #undef TILED_INST
+#undef TILED_INST64
 static const int g_ntiled = int(sizeof(g_tiled) / sizeof(g_tiled[0]));
 
 // ------------------------------------------------------------------------------------------
@@ -120,6 +134,7 @@ struct ndnlm_plan {
     DevParams P;
     int kernel;         // NDNLM_KERNEL_GENERIC / NDNLM_KERNEL_TILED
     int inst;           // index into g_tiled
+    int vec_bytes;      // tiled layout: bytes per staged voxel group, 16 (float4) or 32 (4 doubles)
     int boxmean;        // reference_compiled fast path (nlm_boxmean.cuh): staged like the tiled kernel, inst == -1
     int threads, grid;
     size_t smem;
@@ -140,9 +155,9 @@ static int largest_divisor_leq(int n, int cap) {
 }
 
 // Try to configure tiled instantiation `ti` for the plan's geometry; returns true if it fits.
-static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti) {
+static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti, int elem) {
     DevParams& P = pl->P;
-    if (ti.nv4 != P.nv4) return false;
+    if (ti.elem != elem || ti.nv4 != P.nv4) return false;
     if (ti.fw != P.fr[0] || ti.fr != P.fr[1] || ti.fx != P.fr[2]) return false;
     if (ti.neff != (pl->n_eff >= 0)) return false;
     const int txw = 32 - 2 * ti.fx;
@@ -177,7 +192,7 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti) {
         for (int k = 0; k < 3; ++k)
             if (P.b[k] > 256) ok = false;
         const size_t plane = ((size_t(P.b[0]) * P.b[1] * P.b[2] + 7) / 8) * 8;
-        smem = size_t(ti.nv4) * plane * 16 + ti.exch_bytes + 16 + 16 * size_t(ti.nwarps);
+        smem = size_t(ti.nv4) * plane * (4 * size_t(elem)) + ti.exch_bytes + 16 + 16 * size_t(ti.nwarps);
         fits = ok && smem <= kMaxSmem;
     }
     if (!fits) return false;
@@ -298,13 +313,22 @@ extern "C" int ndnlm_plan_create_roles(ndnlm_plan_t** out_plan, const int64_t sh
     pl->inst = -1;
     // float64 data runs on the tiled kernel only on explicit request (NDNLM_KERNEL_TILED): the cube is then staged as
     // float32 and the result widened back -- north_star's fp32 compute, ~1e-6 from the reference's float64 result.
-    const bool tiled_ok = (dtype == NDNLM_F32 || kernel == NDNLM_KERNEL_TILED) && !P.zero_dist && K > 0;
+    // float64 data: the float64 instantiations of the tiled kernel (the reference's own float64 arithmetic) by default;
+    // NDNLM_KERNEL_TILED asks for the float32 instantiations instead (the cube is staged as float32 and the result
+    // widened back: north_star's fp32 compute, ~1e-6 from the float64 result); NDNLM_KERNEL_TILED_F64 insists on float64.
+    const bool tiled_ok = !P.zero_dist && K > 0;
+    const int elem = (dtype == NDNLM_F64 && kernel != NDNLM_KERNEL_TILED) ? 8 : 4;
+    if (kernel == NDNLM_KERNEL_TILED_F64 && dtype != NDNLM_F64) {
+        delete pl;
+        return fail(NDNLM_EINVAL, "NDNLM_KERNEL_TILED_F64 needs float64 data");
+    }
+    pl->vec_bytes = 4 * elem;
     if (kernel != NDNLM_KERNEL_GENERIC && tiled_ok) {
         const char* venv = getenv("NDNLM_TILED_VARIANT");   // tuning aid: force one instantiation
         const int forced = venv ? atoi(venv) : -1;
         for (int i = 0; i < g_ntiled; ++i) {
             if (forced >= 0 && i != forced) continue;
-            if (configure_tiled(pl, g_tiled[i])) {
+            if (configure_tiled(pl, g_tiled[i], elem)) {
                 pl->kernel = NDNLM_KERNEL_TILED;
                 pl->inst = i;
                 break;
@@ -316,17 +340,18 @@ extern "C" int ndnlm_plan_create_roles(ndnlm_plan_t** out_plan, const int64_t sh
     if (kernel != NDNLM_KERNEL_GENERIC && dtype == NDNLM_F32 && P.zero_dist && n_eff < 0 && K > 0 && boxmean_supported(P)) {
         pl->kernel = NDNLM_KERNEL_TILED;
         pl->boxmean = 1;
+        pl->vec_bytes = 16;
     }
-    if (kernel == NDNLM_KERNEL_TILED && pl->kernel != NDNLM_KERNEL_TILED) {
+    if ((kernel == NDNLM_KERNEL_TILED || kernel == NDNLM_KERNEL_TILED_F64) && pl->kernel != NDNLM_KERNEL_TILED) {
         delete pl;
         return fail(NDNLM_EINVAL, "no tiled-kernel instantiation for this configuration (dtype/V/f pattern/shared memory)");
     }
     const long long voxels = (long long)shape[0] * shape[1] * shape[2];
     const long long pvox = (long long)P.pd[0] * P.pd[1] * P.pd[2];
     if (pl->kernel == NDNLM_KERNEL_TILED) {
-        pl->elem_bytes = 4;
-        pl->padded_bytes = size_t(pvox) * P.nv4 * 16;
-        pl->out_bytes = size_t(voxels) * P.nv4 * 16;
+        pl->elem_bytes = pl->vec_bytes / 4;
+        pl->padded_bytes = size_t(pvox) * P.nv4 * pl->vec_bytes;
+        pl->out_bytes = size_t(voxels) * P.nv4 * pl->vec_bytes;
         if (pl->boxmean) {
             pl->threads = 256;
             pl->grid = 0;
@@ -423,10 +448,12 @@ extern "C" int ndnlm_stage(const ndnlm_plan_t* pl, const void* arr, const int64_
     const long long pvox = (long long)S.pd[0] * S.pd[1] * S.pd[2];
     if (pl->kernel == NDNLM_KERNEL_TILED) {
         const long long total = pvox * S.nv4;
-        if (pl->dtype == NDNLM_F64)
-            stage_tiled_kernel<double><<<blocks_for(total, 256), 256, 0, st>>>(S, (const double*)arr, (float4*)padded);
+        if (pl->vec_bytes == 32)
+            stage_tiled_kernel<double, double4v><<<blocks_for(total, 256), 256, 0, st>>>(S, (const double*)arr, (double4v*)padded);
+        else if (pl->dtype == NDNLM_F64)
+            stage_tiled_kernel<double, float4><<<blocks_for(total, 256), 256, 0, st>>>(S, (const double*)arr, (float4*)padded);
         else
-            stage_tiled_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(S, (const float*)arr, (float4*)padded);
+            stage_tiled_kernel<float, float4><<<blocks_for(total, 256), 256, 0, st>>>(S, (const float*)arr, (float4*)padded);
     } else if (pl->dtype == NDNLM_F64) {
         const long long total = pvox * S.V;
         stage_generic_kernel<double><<<blocks_for(total, 256), 256, 0, st>>>(S, (const double*)arr, (double*)padded);
@@ -448,10 +475,12 @@ extern "C" int ndnlm_unstage(const ndnlm_plan_t* pl, const void* internal, void*
     fill_stage_params(pl, out_strides, S);
     const long long vox = (long long)S.n[0] * S.n[1] * S.n[2];
     if (pl->kernel == NDNLM_KERNEL_TILED) {
-        if (pl->dtype == NDNLM_F64)
-            unstage_tiled_kernel<double><<<blocks_for(vox * S.nv4, 256), 256, 0, st>>>(S, (const float4*)internal, (double*)output);
+        if (pl->vec_bytes == 32)
+            unstage_tiled_kernel<double, double4v><<<blocks_for(vox * S.nv4, 256), 256, 0, st>>>(S, (const double4v*)internal, (double*)output);
+        else if (pl->dtype == NDNLM_F64)
+            unstage_tiled_kernel<double, float4><<<blocks_for(vox * S.nv4, 256), 256, 0, st>>>(S, (const float4*)internal, (double*)output);
         else
-            unstage_tiled_kernel<float><<<blocks_for(vox * S.nv4, 256), 256, 0, st>>>(S, (const float4*)internal, (float*)output);
+            unstage_tiled_kernel<float, float4><<<blocks_for(vox * S.nv4, 256), 256, 0, st>>>(S, (const float4*)internal, (float*)output);
     } else if (pl->dtype == NDNLM_F64) {
         unstage_generic_kernel<double><<<blocks_for(vox * S.V, 256), 256, 0, st>>>(S, (const double*)internal, (double*)output);
     } else {
@@ -470,7 +499,7 @@ static void halo_geometry(const ndnlm_plan* pl, int role, long long& outer, long
     const int generic_order[3] = {ROLE_W, ROLE_R, ROLE_X};
     const int* order;
     if (pl->kernel == NDNLM_KERNEL_TILED) {
-        unit = 16;
+        unit = pl->vec_bytes;
         outer = P.nv4;
         inner = 1;
         order = tiled_order;
@@ -512,7 +541,9 @@ static int halo_copy(const ndnlm_plan* pl, void* padded, int axis, int side, voi
     if (PACK) first = side == 0 ? rows : P.n[role];          // my first / last `pad` interior rows
     else      first = side == 0 ? 0 : rows + P.n[role];      // my lower / upper pad rows
     const long long total = outer * rows * inner;
-    if (unit == 16)
+    if (unit == 32)
+        halo_copy_kernel<double4v, PACK><<<blocks_for(total, 256), 256, 0, st>>>((double4v*)padded, (double4v*)msg, outer, P.pd[role], inner, first, rows);
+    else if (unit == 16)
         halo_copy_kernel<float4, PACK><<<blocks_for(total, 256), 256, 0, st>>>((float4*)padded, (float4*)msg, outer, P.pd[role], inner, first, rows);
     else if (unit == 8)
         halo_copy_kernel<double, PACK><<<blocks_for(total, 256), 256, 0, st>>>((double*)padded, (double*)msg, outer, P.pd[role], inner, first, rows);
@@ -580,18 +611,19 @@ extern "C" int ndnlm_run_scratch(const ndnlm_plan_t* pl, const void* padded, voi
         if (!P.use_ldg_loader) {
             encode_tiled_fn enc = get_encode_fn();
             if (!enc) return fail(NDNLM_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-            // padded cube [q][W][X][R] as a 5-D float tensor (v, r, x, w, q), innermost first
+            // padded cube [q][W][X][R] as a 5-D tensor of floats / doubles (v, r, x, w, q), innermost first
+            const cuuint64_t vb = (cuuint64_t)pl->vec_bytes;
             const cuuint64_t gdim[5] = {4, (cuuint64_t)P.pd[1], (cuuint64_t)P.pd[2], (cuuint64_t)P.pd[0], (cuuint64_t)P.nv4};
-            const cuuint64_t gstr[4] = {16, (cuuint64_t)P.pd[1] * 16, (cuuint64_t)P.pd[1] * P.pd[2] * 16,
-                                        (cuuint64_t)P.pd[1] * P.pd[2] * P.pd[0] * 16};
+            const cuuint64_t gstr[4] = {vb, (cuuint64_t)P.pd[1] * vb, (cuuint64_t)P.pd[1] * P.pd[2] * vb,
+                                        (cuuint64_t)P.pd[1] * P.pd[2] * P.pd[0] * vb};
             const cuuint32_t box[5] = {4, (cuuint32_t)P.b[1], (cuuint32_t)P.b[2], (cuuint32_t)P.b[0], 1};
             const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-            CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(padded), gdim, gstr, box, estr,
+            CUresult cr = enc(&tmap, pl->vec_bytes == 32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(padded), gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (cr != CUDA_SUCCESS) return fail(NDNLM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(cr));
         }
-        cudaError_t e = ti.launch(tmap, P, (const float4*)padded, (float4*)out_internal, err_flag, pl->grid, pl->smem, st);
+        cudaError_t e = ti.launch(tmap, P, padded, out_internal, err_flag, pl->grid, pl->smem, st);
         g_launches++;
         if (e != cudaSuccess) return fail(NDNLM_ECUDA, "tiled kernel launch failed: %s", cudaGetErrorString(e));
     } else if (pl->dtype == NDNLM_F64) {
@@ -636,7 +668,10 @@ extern "C" int ndnlm_apply(const ndnlm_plan_t* pl, const void* arr, const int64_
     int32_t hflag = 0;
     CUDA_TRY(cudaMemcpyAsync(&hflag, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (hflag) return fail(NDNLM_ENOSOLUTION, "No solution");
+    if (hflag & NDNLM_FLAG_NOSOLUTION) return fail(NDNLM_ENOSOLUTION, "No solution");
+    if (hflag & NDNLM_FLAG_UNDERFLOW)
+        return fail(NDNLM_WUNDERFLOW, "at some voxels every neighbour weight is below the float32 range (< 2^-126): they were "
+                                      "left unfiltered; use float64 data / the generic kernel, or a larger h");
     return NDNLM_OK;
 }
 

@@ -2,6 +2,9 @@
 #include "nlm_tiled_launch.cuh"
 
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
-    template cudaError_t launch_tiled<NV4, FW, FX, FR, L, NW, CH, NEFF>(                              \
-        const CUtensorMap&, const ndnlm::DevParams&, const float4*, float4*, int*, int, size_t, cudaStream_t);
+    template cudaError_t launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF>(                       \
+        const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
+#define TILED_INST64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                               \
+    template cudaError_t launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF>(                      \
+        const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
 #include "instances_g2.inc"

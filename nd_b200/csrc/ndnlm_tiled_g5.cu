@@ -1,4 +1,4 @@
-// Explicit instantiations of the tiled kernel, group 0 (instances_g0.inc); see nlm_tiled_launch.cuh.
+// Explicit instantiations of the tiled kernel, group 5 (instances_g5.inc); see nlm_tiled_launch.cuh.
 #include "nlm_tiled_launch.cuh"
 
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
@@ -7,4 +7,4 @@
 #define TILED_INST64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                               \
     template cudaError_t launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF>(                      \
         const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
-#include "instances_g0.inc"
+#include "instances_g5.inc"

@@ -68,7 +68,7 @@ nlm_generic_kernel(const DevParams P, const T* __restrict__ padded, T* __restric
             if (max_w == 0.0) max_w = 1.0;
             ws = max_w;
         } else {
-            if (P.n_eff - 1.0 > total_w * total_w / total_sq) atomicExch(err, 1);
+            if (P.n_eff - 1.0 > total_w * total_w / total_sq) atomicOr(err, 1);
             ws = (total_w + sqrt(P.n_eff * total_w * total_w - P.n_eff * P.n_eff * total_sq + P.n_eff * total_sq)) /
                  (P.n_eff - 1.0);
         }

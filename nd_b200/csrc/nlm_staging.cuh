@@ -12,6 +12,7 @@
 //   generic  [W][R][X][V]   T
 #pragma once
 #include "nlm_common.cuh"
+#include "nlm_tiled.cuh"   // double4v, mk4
 
 namespace ndnlm {
 
@@ -25,8 +26,9 @@ struct StageParams {
                                    // 2 the source array itself extends over them (slab of a larger array)
 };
 
-template <typename TIN>
-__global__ void stage_tiled_kernel(const StageParams S, const TIN* __restrict__ arr, float4* __restrict__ padded) {
+template <typename TIN, typename V4>
+__global__ void stage_tiled_kernel(const StageParams S, const TIN* __restrict__ arr, V4* __restrict__ padded) {
+    using TS = decltype(V4().x);     // float or double: the type the kernel computes in
     const long long plane = (long long)S.pd[0] * S.pd[1] * S.pd[2];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= plane * S.nv4) return;
@@ -51,13 +53,13 @@ __global__ void stage_tiled_kernel(const StageParams S, const TIN* __restrict__ 
         }
         src += (long long)reflect_index(u, S.n[role]) * S.rstride[role];
     }
-    float v[4];
+    TS v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int var = 4 * q + k;
-        v[k] = (var < S.V) ? float(arr[src + var * S.vstride]) : 0.f;
+        v[k] = (var < S.V) ? TS(arr[src + var * S.vstride]) : TS(0);
     }
-    padded[i] = make_float4(v[0], v[1], v[2], v[3]);
+    padded[i] = mk4(v[0], v[1], v[2], v[3]);
 }
 
 template <typename T>
@@ -89,8 +91,9 @@ __global__ void stage_generic_kernel(const StageParams S, const T* __restrict__ 
     padded[i] = arr[src];
 }
 
-template <typename TOUT>
-__global__ void unstage_tiled_kernel(const StageParams S, const float4* __restrict__ internal, TOUT* __restrict__ output) {
+template <typename TOUT, typename V4>
+__global__ void unstage_tiled_kernel(const StageParams S, const V4* __restrict__ internal, TOUT* __restrict__ output) {
+    using TS = decltype(V4().x);
     const long long plane = (long long)S.n[0] * S.n[1] * S.n[2];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= plane * S.nv4) return;
@@ -104,8 +107,8 @@ __global__ void unstage_tiled_kernel(const StageParams S, const float4* __restri
     long long dst = 0;
 #pragma unroll
     for (int role = 0; role < 3; ++role) dst += (long long)ip[role] * S.rstride[role];
-    const float4 v = internal[i];
-    const float vv[4] = {v.x, v.y, v.z, v.w};
+    const V4 v = internal[i];
+    const TS vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int var = 4 * q + k;

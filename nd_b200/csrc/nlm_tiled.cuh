@@ -18,6 +18,11 @@
 //
 // No tensor cores: the path is not a dense contraction.  The binding unit is the FP32 pipe
 // (128 lane-ops/clk/SM, profiles/r1_pipe_microbench.txt).
+//
+// The kernel is templated on the element type T.  T = float is the path described above.  T = double is the
+// reference's float64 arithmetic (fused `floating` = double, nd/_filters.pyx:320-321: differences, squares, patch
+// sums, weights with a double-precision exp, weighted sums all in float64) on the same tiles: 32-byte voxels
+// (4 doubles), plain FP64 instructions instead of the packed f32x2 ones, half the warps per CTA.
 #pragma once
 #include <type_traits>
 
@@ -95,9 +100,46 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
+// ---- element-type traits: float -> float4 / float2 with packed f32x2 arithmetic, double -> 4 / 2 doubles ----
+struct alignas(32) double4v { double x, y, z, w; };
+__device__ __forceinline__ double2 lo2(const double4v& v) { return make_double2(v.x, v.y); }
+__device__ __forceinline__ double2 hi2(const double4v& v) { return make_double2(v.z, v.w); }
+
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    using V4 = float4;
+    using P2 = float2;
+    static constexpr CUtensorMapDataType tma_type = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+};
+template <> struct Elem<double> {
+    using V4 = double4v;
+    using P2 = double2;
+    static constexpr CUtensorMapDataType tma_type = CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+};
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
+__device__ __forceinline__ float4 mk4(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+__device__ __forceinline__ double4v mk4(double a, double b, double c, double d) { double4v v; v.x = a; v.y = b; v.z = c; v.w = d; return v; }
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ double2 padd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ double2 pfma(double2 a, double2 b, double2 c) { return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 pneg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ double2 pneg(double2 a) { return make_double2(-a.x, -a.y); }
+// NaN-propagating max(x, 0) like the reference's `0 > x ? 0 : x`
+__device__ __forceinline__ float clamp0_nan(float x) { return fmax_nan(x, 0.f); }
+__device__ __forceinline__ double clamp0_nan(double x) { return (0.0 > x) ? 0.0 : x; }
+// weight from the scaled, clamped exponent argument: float: exp2(-t) (t carries log2 e), double: exp(-t)
+__device__ __forceinline__ float weight_of(float t) { return ex2_approx(-t); }
+__device__ __forceinline__ double weight_of(double t) { return exp(-t); }
+__device__ __forceinline__ float tmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double tmax(double a, double b) { return fmax(a, b); }
+
 // Direct (2F+1)-term sum along the register column, fixed order.
-template <int F, int L>
-__device__ __forceinline__ void column_box_sum(const float (&s)[L + 2 * F], float (&o)[L]) {
+template <int F, int L, typename T>
+__device__ __forceinline__ void column_box_sum(const T (&s)[L + 2 * F], T (&o)[L]) {
     if constexpr (F == 0) {
 #pragma unroll
         for (int i = 0; i < L; ++i) o[i] = s[i];
@@ -105,7 +147,7 @@ __device__ __forceinline__ void column_box_sum(const float (&s)[L + 2 * F], floa
 #pragma unroll
         for (int i = 0; i < L; ++i) o[i] = (s[i] + s[i + 1]) + s[i + 2];
     } else if constexpr (F == 2) {
-        float a[L + 3];
+        T a[L + 3];
 #pragma unroll
         for (int i = 0; i < L + 3; ++i) a[i] = s[i] + s[i + 1];
 #pragma unroll
@@ -113,7 +155,7 @@ __device__ __forceinline__ void column_box_sum(const float (&s)[L + 2 * F], floa
     } else {
 #pragma unroll
         for (int i = 0; i < L; ++i) {
-            float t = s[i];
+            T t = s[i];
 #pragma unroll
             for (int d = 1; d <= 2 * F; ++d) t += s[i + d];
             o[i] = t;
@@ -124,11 +166,11 @@ __device__ __forceinline__ void column_box_sum(const float (&s)[L + 2 * F], floa
 // F == 1 variant that shares the middle pair between two neighbouring outputs: 3 adds per 2 outputs
 // instead of 4.  The association depends on the parity of the output index inside the column, so it is
 // only used where the R axis is never cut by slabs / shards (three filtered axes: W is axis 0).
-template <int L>
-__device__ __forceinline__ void column_box_sum_paired(const float (&s)[L + 2], float (&o)[L]) {
+template <int L, typename T>
+__device__ __forceinline__ void column_box_sum_paired(const T (&s)[L + 2], T (&o)[L]) {
 #pragma unroll
     for (int k = 0; k < L / 2; ++k) {
-        const float m = s[2 * k + 1] + s[2 * k + 2];
+        const T m = s[2 * k + 1] + s[2 * k + 2];
         o[2 * k] = s[2 * k] + m;
         o[2 * k + 1] = m + s[2 * k + 3];
     }
@@ -175,45 +217,49 @@ __device__ __forceinline__ void dispatch_chunk(const int nj, const bool centre, 
 }
 
 // The same for two values at once (a register pair): the adds are packed FADD2.
-template <int F>
-__device__ __forceinline__ float2 lane_box_sum2(const float2 v) {
-    auto up = [](const float2 a, const int d) {
-        return make_float2(__shfl_up_sync(FULL_MASK, a.x, d), __shfl_up_sync(FULL_MASK, a.y, d));
+template <int F, typename P2>
+__device__ __forceinline__ P2 lane_box_sum2(const P2 v) {
+    auto up = [](const P2 a, const int d) {
+        return mk2(__shfl_up_sync(FULL_MASK, a.x, d), __shfl_up_sync(FULL_MASK, a.y, d));
     };
-    auto down = [](const float2 a, const int d) {
-        return make_float2(__shfl_down_sync(FULL_MASK, a.x, d), __shfl_down_sync(FULL_MASK, a.y, d));
+    auto down = [](const P2 a, const int d) {
+        return mk2(__shfl_down_sync(FULL_MASK, a.x, d), __shfl_down_sync(FULL_MASK, a.y, d));
     };
     if constexpr (F == 0) {
         return v;
     } else if constexpr (F == 1) {
-        const float2 a = up(v, 1), b = down(v, 1);
-        return __fadd2_rn(__fadd2_rn(a, v), b);
+        const P2 a = up(v, 1), b = down(v, 1);
+        return padd(padd(a, v), b);
     } else if constexpr (F == 2) {
-        const float2 pair = __fadd2_rn(v, down(v, 1));
-        const float2 left = up(pair, 2), right = down(v, 2);
-        return __fadd2_rn(__fadd2_rn(left, pair), right);
+        const P2 pair = padd(v, down(v, 1));
+        const P2 left = up(pair, 2), right = down(v, 2);
+        return padd(padd(left, pair), right);
     } else {
-        float2 t = v;
+        P2 t = v;
 #pragma unroll
-        for (int d = 1; d <= F; ++d) t = __fadd2_rn(t, __fadd2_rn(up(v, d), down(v, d)));
+        for (int d = 1; d <= F; ++d) t = padd(t, padd(up(v, d), down(v, d)));
         return t;
     }
 }
 
-template <int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
+template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
 struct TiledCfg {
     static constexpr int E = L + 2 * FR;      // column elements including the patch halo
     static constexpr int WN = E + CH - 1;     // neighbour window elements per chunk of CH R-offsets
     static constexpr int TXW = 32 - 2 * FX;   // valid lanes per warp
     static constexpr int THREADS = NWARPS * 32;
-    static constexpr size_t EXCH_BYTES = FW > 0 ? size_t(CH) * NWARPS * (L / 2) * 32 * sizeof(float2) : 0;
+    static constexpr size_t EXCH_BYTES = FW > 0 ? size_t(CH) * NWARPS * (L / 2) * 32 * sizeof(typename Elem<T>::P2) : 0;
 };
 
-template <int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
+template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
-                 const float4* __restrict__ padded, float4* __restrict__ out, int* __restrict__ err) {
-    using Cfg = TiledCfg<NV4, FW, FX, FR, L, NWARPS, CH, NEFF>;
+                 const typename Elem<T>::V4* __restrict__ padded, typename Elem<T>::V4* __restrict__ out,
+                 int* __restrict__ err) {
+    using Cfg = TiledCfg<T, NV4, FW, FX, FR, L, NWARPS, CH, NEFF>;
+    using V4 = typename Elem<T>::V4;
+    using P2 = typename Elem<T>::P2;
+    constexpr bool F64 = sizeof(T) == 8;
     static_assert(L % 2 == 0, "L must be even (outputs are exchanged in pairs)");
     constexpr int E = Cfg::E, TXW = Cfg::TXW;
 
@@ -223,10 +269,10 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int BW = P.b[0], BRP = P.b[1], BX = P.b[2];
     const int plane = ((BW * BRP * BX + 7) >> 3) << 3;   // float4 per variable group, 128-B multiple
-    float4* tile = reinterpret_cast<float4*>(smem_raw);
-    float2* exch = reinterpret_cast<float2*>(smem_raw + size_t(NV4) * plane * sizeof(float4));
+    V4* tile = reinterpret_cast<V4*>(smem_raw);
+    P2* exch = reinterpret_cast<P2*>(smem_raw + size_t(NV4) * plane * sizeof(V4));
     uint64_t* mbar =
-        reinterpret_cast<uint64_t*>(smem_raw + size_t(NV4) * plane * sizeof(float4) + Cfg::EXCH_BYTES);
+        reinterpret_cast<uint64_t*>(smem_raw + size_t(NV4) * plane * sizeof(V4) + Cfg::EXCH_BYTES);
     // Neighbour-only synchronisation of the W exchange (no CTA-wide barrier in the hot loop):
     //   full[w]   every row that warp w reads has published its sums for the current chunk (one arrival per
     //             source row, so a reader waits ONCE)
@@ -266,7 +312,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         const int wbase = w0 + pass * P.ntw_pass;
         if (!P.use_ldg_loader) {
             if (threadIdx.x == 0) {
-                mbar_arrive_expect_tx(mbar, uint32_t(NV4) * uint32_t(BW * BRP * BX) * 16u);
+                mbar_arrive_expect_tx(mbar, uint32_t(NV4) * uint32_t(BW * BRP * BX) * uint32_t(sizeof(V4)));
 #pragma unroll
                 for (int q = 0; q < NV4; ++q) tma_load_5d(tile + size_t(q) * plane, &tmap, mbar, 0, r0, x0, wbase, q);
             }
@@ -281,7 +327,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 const int bx = rem % BX;
                 const int bw = rem / BX;
                 const int gw = wbase + bw, gr = r0 + br, gx = x0 + bx;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                V4 v = mk4(T(0), T(0), T(0), T(0));
                 if (gw < P.pd[0] && gr < P.pd[1] && gx < P.pd[2])
                     v = padded[((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr];
                 tile[size_t(q) * plane + (bw * BX + bx) * BRP + br] = v;
@@ -301,7 +347,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     const bool wvalid = (FW == 0) || (ww >= FW && ww < NWARPS - FW);
 
     // centre column: read once, straight from the padded cube (R is the fastest axis there too)
-    float4 c[NV4][E];
+    V4 c[NV4][E];
     {
         const int gw = w0 + ww + P.rad[0], gx = x0 + lx;      // padded coordinates of this thread's column
         const bool inb = gw < P.pd[0] && gx < P.pd[2];
@@ -311,39 +357,43 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
             for (int e = 0; e < E; ++e) {
                 const int gr = r0 + lr0 + e;
                 c[q][e] = (inb && gr < P.pd[1])
-                              ? __ldg(padded + ((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                              ? padded[((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr]
+                              : mk4(T(0), T(0), T(0), T(0));
             }
     }
 
-    float2 acc_lo[NV4][L], acc_hi[NV4][L];
-    float2 S2[L / 2], Q2[L / 2];
-    float M[L];
+    P2 acc_lo[NV4][L], acc_hi[NV4][L];
+    P2 S2[L / 2], Q2[L / 2];
+    T M[L];
     NDNLM_FOLD_T Sd[L], Qd[L];
 #pragma unroll
     for (int o = 0; o < L; ++o) {
 #pragma unroll
         for (int q = 0; q < NV4; ++q) {
-            acc_lo[q][o] = make_float2(0.f, 0.f);
-            acc_hi[q][o] = make_float2(0.f, 0.f);
+            acc_lo[q][o] = mk2(T(0), T(0));
+            acc_hi[q][o] = mk2(T(0), T(0));
         }
-        M[o] = 0.f;
+        M[o] = T(0);
         Sd[o] = 0;
         Qd[o] = 0;
     }
 
 #pragma unroll
     for (int o2 = 0; o2 < L / 2; ++o2) {
-        S2[o2] = make_float2(0.f, 0.f);
-        Q2[o2] = make_float2(0.f, 0.f);
+        S2[o2] = mk2(T(0), T(0));
+        Q2[o2] = mk2(T(0), T(0));
     }
     const int rW = P.rad[0], rR = P.rad[1], rX = P.rad[2];
-    const float2 c1 = make_float2(P.c1, P.c1);
-    const float2 nc2 = make_float2(-P.c2, -P.c2);
-    float2* const ex_own = exch + (wid * (L / 2)) * 32 + lane;     // + (j*NWARPS*(L/2) + o2)*32
+    // exponent argument t = D c1 - c2: float carries log2(e) (exp2 path), double is the reference's
+    // (D / norm - 2 sigma^2) / h^2 (nd/_filters.pyx:388-391)
+    const T c1s = F64 ? T(P.inv_norm * P.inv_h2) : T(P.c1);
+    const T c2s = F64 ? T(P.two_sigma2 * P.inv_h2) : T(P.c2);
+    const P2 c1 = mk2(c1s, c1s);
+    const P2 nc2 = mk2(-c2s, -c2s);
+    P2* const ex_own = exch + (wid * (L / 2)) * 32 + lane;     // + (j*NWARPS*(L/2) + o2)*32
     constexpr int EX_J = NWARPS * (L / 2) * 32;                     // float2 stride between R-offsets j
     constexpr int EX_ROW = (L / 2) * 32;                            // float2 stride between W rows (FW>0: 1 warp/row)
-    [[maybe_unused]] float4* const ex_own4 = reinterpret_cast<float4*>(exch) + wid * 32 + lane;   // L == 4 layout
+    [[maybe_unused]] V4* const ex_own4 = reinterpret_cast<V4*>(exch) + wid * 32 + lane;   // L == 4 layout
     [[maybe_unused]] constexpr int EX_J4 = NWARPS * 32;             // float4 stride between R-offsets j
     uint32_t xpar = 0;                                              // parity of the current exchange round
     static_assert(FW == 0 || NWARPS >= 2 * FW + 2, "every row needs at least one reader");
@@ -351,39 +401,39 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     // One chunk of NJ consecutive R-offsets [ch0, ch0+NJ).  NJ is a compile-time constant so the body is
     // straight-line code the scheduler can interleave freely.  CENTRE: the chunk contains the centre
     // voxel itself (tw = tx = 0 and ch0 <= 0 < ch0+NJ), whose offset must be skipped -- rare slow path.
-    auto chunk = [&](auto nj_tag, auto centre_tag, const float4* nb, const int ch0) {
+    auto chunk = [&](auto nj_tag, auto centre_tag, const V4* nb, const int ch0) {
         constexpr int NJ = decltype(nj_tag)::value;
         constexpr bool CENTRE = decltype(centre_tag)::value;
         constexpr int WNJ = E + NJ - 1;
         if constexpr (CENTRE && FW > 0 && !NDNLM_DEBUG_CTA_SYNC) mbar_wait(mbar_empty + wid, xpar ^ 1);
-        [[maybe_unused]] float2 own[NDNLM_KEEP_OWN != 0 ? NJ : 1][L / 2];
+        [[maybe_unused]] P2 own[NDNLM_KEEP_OWN != 0 ? NJ : 1][L / 2];
 
-        float4 n[NV4][WNJ];
+        V4 n[NV4][WNJ];
 #pragma unroll
         for (int k = 0; k < WNJ; ++k) {
 #pragma unroll
             for (int q = 0; q < NV4; ++q) n[q][k] = nb[size_t(q) * plane + k];
         }
 
-        auto weigh = [&](const float2 (&D)[L / 2], const int j) {
+        auto weigh = [&](const P2 (&D)[L / 2], const int j) {
 #pragma unroll
             for (int o2 = 0; o2 < L / 2; ++o2) {
-                const float2 t = __ffma2_rn(D[o2], c1, nc2);
-                const float w0_ = ex2_approx(-fmax_nan(t.x, 0.f));
-                const float w1_ = ex2_approx(-fmax_nan(t.y, 0.f));
+                const P2 t = pfma(D[o2], c1, nc2);
+                const T w0_ = weight_of(clamp0_nan(t.x));
+                const T w1_ = weight_of(clamp0_nan(t.y));
                 const int o = 2 * o2;
-                const float2 w2 = make_float2(w0_, w1_);
-                S2[o2] = __fadd2_rn(S2[o2], w2);
-                M[o] = fmaxf(M[o], w0_);
-                M[o + 1] = fmaxf(M[o + 1], w1_);
-                if constexpr (NEFF) Q2[o2] = __ffma2_rn(w2, w2, Q2[o2]);
-                const float2 w0b = make_float2(w0_, w0_), w1b = make_float2(w1_, w1_);
+                const P2 w2 = mk2(w0_, w1_);
+                S2[o2] = padd(S2[o2], w2);
+                M[o] = tmax(M[o], w0_);
+                M[o + 1] = tmax(M[o + 1], w1_);
+                if constexpr (NEFF) Q2[o2] = pfma(w2, w2, Q2[o2]);
+                const P2 w0b = mk2(w0_, w0_), w1b = mk2(w1_, w1_);
 #pragma unroll
                 for (int q = 0; q < NV4; ++q) {
-                    acc_lo[q][o] = __ffma2_rn(w0b, lo2(n[q][o + FR + j]), acc_lo[q][o]);
-                    acc_hi[q][o] = __ffma2_rn(w0b, hi2(n[q][o + FR + j]), acc_hi[q][o]);
-                    acc_lo[q][o + 1] = __ffma2_rn(w1b, lo2(n[q][o + 1 + FR + j]), acc_lo[q][o + 1]);
-                    acc_hi[q][o + 1] = __ffma2_rn(w1b, hi2(n[q][o + 1 + FR + j]), acc_hi[q][o + 1]);
+                    acc_lo[q][o] = pfma(w0b, lo2(n[q][o + FR + j]), acc_lo[q][o]);
+                    acc_hi[q][o] = pfma(w0b, hi2(n[q][o + FR + j]), acc_hi[q][o]);
+                    acc_lo[q][o + 1] = pfma(w1b, lo2(n[q][o + 1 + FR + j]), acc_lo[q][o + 1]);
+                    acc_hi[q][o + 1] = pfma(w1b, hi2(n[q][o + 1 + FR + j]), acc_hi[q][o + 1]);
                 }
             }
         };
@@ -394,26 +444,25 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
             if constexpr (CENTRE) {
                 if (ch0 + j == 0) continue;   // p == q is excluded (nd/_filters.pyx:368-369)
             }
-            float s[E];
+            T s[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                float2 sq;
+                P2 sq;
 #pragma unroll
                 for (int q = 0; q < NV4; ++q) {
-                    const float2 nlo = lo2(n[q][e + j]), nhi = hi2(n[q][e + j]);
-                    const float2 d0 = __fadd2_rn(lo2(c[q][e]), make_float2(-nlo.x, -nlo.y));
-                    const float2 d1 = __fadd2_rn(hi2(c[q][e]), make_float2(-nhi.x, -nhi.y));
-                    sq = (q == 0) ? __fmul2_rn(d0, d0) : __ffma2_rn(d0, d0, sq);
-                    sq = __ffma2_rn(d1, d1, sq);
+                    const P2 d0 = padd(lo2(c[q][e]), pneg(lo2(n[q][e + j])));
+                    const P2 d1 = padd(hi2(c[q][e]), pneg(hi2(n[q][e + j])));
+                    sq = (q == 0) ? pmul(d0, d0) : pfma(d0, d0, sq);
+                    sq = pfma(d1, d1, sq);
                 }
                 s[e] = sq.x + sq.y;
             }
-            float pr[L];
+            T pr[L];
             if constexpr (FR == 1 && FW > 0) column_box_sum_paired<L>(s, pr);
             else column_box_sum<FR, L>(s, pr);
-            float2 px[L / 2];
+            P2 px[L / 2];
 #pragma unroll
-            for (int o2 = 0; o2 < L / 2; ++o2) px[o2] = lane_box_sum2<FX>(make_float2(pr[2 * o2], pr[2 * o2 + 1]));
+            for (int o2 = 0; o2 < L / 2; ++o2) px[o2] = lane_box_sum2<FX>(mk2(pr[2 * o2], pr[2 * o2 + 1]));
             if constexpr (FW == 0) {
                 weigh(px, j);
             } else {
@@ -424,7 +473,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 }
                 if constexpr (L == 4) {
                     // one 16-B store / load per row and offset: [j][row][lane] float4
-                    ex_own4[j * EX_J4] = make_float4(px[0].x, px[0].y, px[1].x, px[1].y);
+                    ex_own4[j * EX_J4] = mk4(px[0].x, px[0].y, px[1].x, px[1].y);
                 } else {
 #pragma unroll
                     for (int o2 = 0; o2 < L / 2; ++o2) ex_own[j * EX_J + o2 * 32] = px[o2];
@@ -452,30 +501,30 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                     if constexpr (CENTRE) {
                         if (ch0 + j == 0) continue;
                     }
-                    float2 D[L / 2];
+                    P2 D[L / 2];
                     if constexpr (L == 4) {
-                        float4 t = ex_own4[j * EX_J4 - FW * 32];
-                        D[0] = make_float2(t.x, t.y);
-                        D[1] = make_float2(t.z, t.w);
+                        V4 t = ex_own4[j * EX_J4 - FW * 32];
+                        D[0] = mk2(t.x, t.y);
+                        D[1] = mk2(t.z, t.w);
 #pragma unroll
                         for (int d = -FW + 1; d <= FW; ++d) {
                             if (NDNLM_KEEP_OWN != 0 && d == 0) {
-                                D[0] = __fadd2_rn(D[0], own[j][0]);
-                                D[1] = __fadd2_rn(D[1], own[j][1]);
+                                D[0] = padd(D[0], own[j][0]);
+                                D[1] = padd(D[1], own[j][1]);
                             } else {
                                 t = ex_own4[j * EX_J4 + d * 32];
-                                D[0] = __fadd2_rn(D[0], make_float2(t.x, t.y));
-                                D[1] = __fadd2_rn(D[1], make_float2(t.z, t.w));
+                                D[0] = padd(D[0], mk2(t.x, t.y));
+                                D[1] = padd(D[1], mk2(t.z, t.w));
                             }
                         }
                     } else {
 #pragma unroll
                         for (int o2 = 0; o2 < L / 2; ++o2) {
-                            float2 t = ex_own[j * EX_J + o2 * 32 - FW * EX_ROW];
+                            P2 t = ex_own[j * EX_J + o2 * 32 - FW * EX_ROW];
 #pragma unroll
                             for (int d = -FW + 1; d <= FW; ++d) {
-                                if (NDNLM_KEEP_OWN != 0 && d == 0) t = __fadd2_rn(t, own[j][o2]);
-                                else t = __fadd2_rn(t, ex_own[j * EX_J + o2 * 32 + d * EX_ROW]);
+                                if (NDNLM_KEEP_OWN != 0 && d == 0) t = padd(t, own[j][o2]);
+                                else t = padd(t, ex_own[j * EX_J + o2 * 32 + d * EX_ROW]);
                             }
                             D[o2] = t;
                         }
@@ -501,11 +550,11 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         for (int o2 = 0; o2 < L / 2; ++o2) {
             Sd[2 * o2] += NDNLM_FOLD_T(S2[o2].x);
             Sd[2 * o2 + 1] += NDNLM_FOLD_T(S2[o2].y);
-            S2[o2] = make_float2(0.f, 0.f);
+            S2[o2] = mk2(T(0), T(0));
             if constexpr (NEFF) {
                 Qd[2 * o2] += NDNLM_FOLD_T(Q2[o2].x);
                 Qd[2 * o2 + 1] += NDNLM_FOLD_T(Q2[o2].y);
-                Q2[o2] = make_float2(0.f, 0.f);
+                Q2[o2] = mk2(T(0), T(0));
             }
         }
     };
@@ -519,7 +568,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
             dispatch_chunk<CH>(nR, false, [&](auto nj_tag, auto) {
                 for (int tw = twa; tw <= twb; ++tw) {
                     for (int tx = -rX; tx <= rX; ++tx) {
-                        const float4* nb0 = tile + ((ww + tw - twa) * BX + lx + tx) * BRP + lr0 - rR;
+                        const V4* nb0 = tile + ((ww + tw - twa) * BX + lx + tx) * BRP + lr0 - rR;
                         if ((tw == 0) & (tx == 0)) chunk(nj_tag, std::true_type{}, nb0, -rR);
                         else chunk(nj_tag, std::false_type{}, nb0, -rR);
                     }
@@ -529,7 +578,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         } else {
             for (int tw = twa; tw <= twb; ++tw) {
                 for (int tx = -rX; tx <= rX; ++tx) {
-                    const float4* nb0 = tile + ((ww + tw - twa) * BX + lx + tx) * BRP + lr0;
+                    const V4* nb0 = tile + ((ww + tw - twa) * BX + lx + tx) * BRP + lr0;
                     const bool centre_step = (tw == 0) & (tx == 0);
                     for (int ch0 = -rR; ch0 <= rR; ch0 += CH) {
                         const int nj = min(CH, rR - ch0 + 1);                        // uniform
@@ -548,30 +597,39 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     const int gw_ = w0 + ww - FW;
     const int gx_ = x0 + wx * TXW + lane - FX;
     if (wvalid && lane >= FX && lane < 32 - FX && gw_ < P.n[0] && gx_ < P.n[2]) {
-        float4* po = out + (size_t(gw_) * P.n[2] + gx_) * P.n[1] + (r0 + wr * L);   // out is [q][W][X][R]
+        V4* po = out + (size_t(gw_) * P.n[2] + gx_) * P.n[1] + (r0 + wr * L);   // out is [q][W][X][R]
         const size_t oplane = size_t(P.n[0]) * P.n[1] * P.n[2];
 #pragma unroll
         for (int o = 0; o < L; ++o) {
             const int gr_ = r0 + wr * L + o;
             if (gr_ >= P.n[1]) continue;
             double ws;
+            // Every neighbour weight below 2^-126 flushes to zero in fp32 (ex2.approx.ftz): the float64 weights of the
+            // reference would still be positive there.  Such a voxel is left unfiltered (self weight 1) and reported
+            // through bit 1 of the flag instead of silently producing 0 / 0 (domain note).
+            const bool underflow = (double(Sd[o]) == 0.0);
+            if (underflow) atomicOr(err, 2);
             if constexpr (NEFF) {
                 const double n_ = P.n_eff, Sx = double(Sd[o]), Qx = double(Qd[o]);
-                if (n_ - 1.0 > Sx * Sx / Qx) atomicExch(err, 1);   // find_weight: 'No solution' (:310-311)
-                ws = (Sx + sqrt(n_ * Sx * Sx - n_ * n_ * Qx + n_ * Qx)) / (n_ - 1.0);
+                if (underflow) {
+                    ws = 1.0;
+                } else {
+                    if (n_ - 1.0 > Sx * Sx / Qx) atomicOr(err, 1);   // find_weight: 'No solution' (:310-311)
+                    ws = (Sx + sqrt(n_ * Sx * Sx - n_ * n_ * Qx + n_ * Qx)) / (n_ - 1.0);
+                }
             } else {
-                ws = (M[o] == 0.f) ? 1.0 : double(M[o]);
+                ws = (M[o] == T(0)) ? 1.0 : double(M[o]);
             }
             const double tot = double(Sd[o]) + ws;
 #pragma unroll
             for (int q = 0; q < NV4; ++q) {
-                const float4 cc = c[q][o + FR];
-                float4 res;
-                // weighted_sum is float32 in the reference and is rounded after the self term (:419)
-                res.x = float(double(float(double(acc_lo[q][o].x) + ws * double(cc.x))) / tot);
-                res.y = float(double(float(double(acc_lo[q][o].y) + ws * double(cc.y))) / tot);
-                res.z = float(double(float(double(acc_hi[q][o].x) + ws * double(cc.z))) / tot);
-                res.w = float(double(float(double(acc_hi[q][o].y) + ws * double(cc.w))) / tot);
+                const V4 cc = c[q][o + FR];
+                V4 res;
+                // weighted_sum has the data type in the reference and is rounded after the self term (:419)
+                res.x = T(double(T(double(acc_lo[q][o].x) + ws * double(cc.x))) / tot);
+                res.y = T(double(T(double(acc_lo[q][o].y) + ws * double(cc.y))) / tot);
+                res.z = T(double(T(double(acc_hi[q][o].x) + ws * double(cc.z))) / tot);
+                res.w = T(double(T(double(acc_hi[q][o].y) + ws * double(cc.w))) / tot);
                 po[q * oplane + o] = res;
             }
         }

@@ -376,6 +376,7 @@ class NLMeansFilter(Filter):
     """
 
     per_variable = False
+    _supports_njobs = True      # njobs = GPUs: y-shards with an r+f halo (nd_b200/shard.py, nd_b200/_filters.py)
 
     def __init__(self, dims=('y', 'x'), r=1, sigma=1, h=1, f=1, n_eff=-1, *, semantics=None, kernel='auto'):
         if isinstance(r, (int, float)):

@@ -21,6 +21,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import torch
 
+from . import _lib
 from . import device as dev
 from .shard import ShardPlan
 
@@ -250,8 +251,7 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
     for s in (s_h2d, s_comp, s_d2h):
         cur.wait_stream(s)
     cur.synchronize()
-    if int(flag.item()):
-        raise ValueError('No solution')
+    _lib.check_flag(flag.item())
     return sp.nshards
 
 
@@ -324,6 +324,5 @@ def apply_device_streamed(source, sink, n0, inner_shape, r3, f3, sigma, h, n_eff
             on_kernel(False, plan)
         plan.unstage(internal, a_out)
         sink(lo, hi, a_out)
-    if int(flag.item()):
-        raise ValueError('No solution')
+    _lib.check_flag(flag.item())
     return sp.nshards

@@ -112,6 +112,42 @@ def test_float64_matches_oracle(dev, c_oracle, shape, r, f):
         assert out.dtype == np.float64 and scaled_err(out, ref) < TOL64, (plan.kernel_name, sem)
 
 
+@pytest.mark.parametrize("shape,r,f", [CASES[0], CASES[1], CASES[2], CASES[3], CASES[4], CASES[5], CASES[6], CASES[7],
+                                       CASES[8], CASES[9], ((40, 70, 33, 4), (5, 5, 2), (1, 1, 1))])
+def test_float64_tiled_kernel_matches_oracle_to_1e12(dev, c_oracle, shape, r, f):
+    """float64 data (every fixture of the reference, nd/testing.py:68-69) runs on the float64 instantiations of the
+    tiled kernel: the reference's own float64 arithmetic (nd/_filters.pyx:320-321), <= 1e-12 from the oracle."""
+    a = sar_like(shape, seed=17 + sum(shape), dtype=np.float64)
+    ref = c_oracle.nlmeans(a, r, f, 0.3, 0.6, threads=8)
+    out, plan = run_plan(dev, a, r, f, 0.3, 0.6)
+    assert plan.is_tiled and "double" in plan.kernel_name, plan.kernel_name
+    assert out.dtype == np.float64 and scaled_err(out, ref) < TOL64, plan.kernel_name
+    out_g, plan_g = run_plan(dev, a, r, f, 0.3, 0.6, kernel="generic")
+    assert "generic" in plan_g.kernel_name and scaled_err(out_g, ref) < TOL64
+
+
+def test_float64_tiled_neff_strided_and_sharded(dev, c_oracle):
+    from nd_b200._filters import _pixelwise_nlmeans_3d
+    a = sar_like((60, 40, 9, 4), seed=23, dtype=np.float64)
+    r, f = (2, 2, 1), (1, 1, 1)
+    ref = c_oracle.nlmeans(a, r, f, 0.3, 1.5, n_eff=6.0, threads=8)
+    out, plan = run_plan(dev, a, r, f, 0.3, 1.5, n_eff=6.0)
+    assert "double" in plan.kernel_name and scaled_err(out, ref) < TOL64
+    with pytest.raises(ValueError, match="No solution"):
+        run_plan(dev, a, (1, 1, 1), (0, 0, 0), 0.01, 0.01, n_eff=20.0)
+    vm = np.moveaxis(np.ascontiguousarray(np.moveaxis(a, -1, 0)), 0, -1)           # variable-major view
+    whole = np.empty_like(vm)
+    _pixelwise_nlmeans_3d(vm, whole, np.array(r, np.uint32), np.array(f, np.uint32), 0.3, 0.6)
+    ref2 = c_oracle.nlmeans(a, r, f, 0.3, 0.6, threads=8)
+    assert scaled_err(whole, ref2) < TOL64
+    parts = np.full_like(vm, np.nan)
+    _pixelwise_nlmeans_3d(vm, parts, np.array(r, np.uint32), np.array(f, np.uint32), 0.3, 0.6, devices=[0, 0], pipeline=False)
+    assert np.array_equal(parts, whole)                                           # halo rows as 32-byte voxels
+    piped = np.full_like(vm, np.nan)
+    _pixelwise_nlmeans_3d(vm, piped, np.array(r, np.uint32), np.array(f, np.uint32), 0.3, 0.6, pipeline=True, slab_rows=24)
+    assert np.array_equal(piped, whole)
+
+
 @pytest.mark.parametrize("shape,r,f", [CASES[1], CASES[4], CASES[10]])
 def test_float64_data_on_the_fp32_tiled_kernel_on_request(dev, c_oracle, shape, r, f):
     """kernel='tiled' with float64 data: staged as float32, result widened back -- north_star's fp32 compute, far
@@ -160,6 +196,16 @@ def test_neff_no_solution_raises_value_error(dev):
     a = sar_like((8, 9, 6, 2), seed=6, dtype=np.float32)
     with pytest.raises(ValueError, match="No solution"):      # nd/_filters.pyx:310-311
         run_plan(dev, a, (1, 1, 1), (0, 0, 0), 0.01, 0.01, n_eff=20.0)
+
+
+def test_weights_below_the_fp32_range_warn_instead_of_nan(dev):
+    """with h so small that every neighbour weight flushes to zero in fp32 the voxel used to come out as
+    0/0 (n_eff >= 0) or silently unfiltered.  Now: unfiltered AND a RuntimeWarning (flag bit 1), never a NaN."""
+    a = sar_like((12, 40, 9, 4), seed=9, dtype=np.float32)
+    for n_eff in (-1, 6.0):
+        with pytest.warns(RuntimeWarning, match="float32 range"):
+            out, plan = run_plan(dev, a, (2, 2, 1), (1, 1, 1), 0.001, 0.005, n_eff=n_eff, kernel="tiled")
+        assert plan.is_tiled and np.array_equal(out, a)
 
 
 def test_nan_footprint_matches_reference(dev, c_oracle):

@@ -203,6 +203,25 @@ def test_gaussian_filter_equals_scipy(dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.int32, np.uint16])
+def test_integer_rasters_equal_scipy(dtype):
+    """scipy accepts integer rasters (double arithmetic, output stored in the input dtype with a C cast -- for the
+    Gaussian after EVERY 1-D pass); ADVICE r1 asked for the same instead of a TypeError."""
+    rng = np.random.default_rng(7)
+    hi = 200 if dtype == np.uint8 else 3000
+    a = rng.integers(0, hi, size=(40, 33, 5)).astype(dtype)
+    k = rng.uniform(0, 1, size=(3, 5, 1))
+    k /= k.sum()
+    assert np.array_equal(_ndimage.convolve(a, k), sn.convolve(a, k))
+    assert np.array_equal(_ndimage.correlate1d(a, [0.25, 0.5, 0.25], axis=1), sn.correlate1d(a, [0.25, 0.5, 0.25], axis=1))
+    got, want = _ndimage.gaussian_filter(a, [1.0, 1.5, 0]), sn.gaussian_filter(a, [1.0, 1.5, 0])
+    assert got.dtype == dtype and np.array_equal(got, want)
+    out = np.empty_like(a)
+    _ndimage.gaussian_filter(a, 1.2, output=out, mode='nearest')
+    assert np.array_equal(out, sn.gaussian_filter(a, 1.2, mode='nearest'))
+
+
+@pytest.mark.gpu
 def test_strided_views_and_output_argument():
     base = _rand((12, 20, 6), np.float64, seed=13)
     a = base.transpose(2, 0, 1)[:, ::2, 1:]                           # non-contiguous view

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""Development timing (GPU) of the generic one-thread-per-voxel kernel (float64 data / float32 data forced generic)."""
+"""Development timing (GPU): float64 data on the float64 tiled kernel, the generic kernel, and the fp32 tiled kernel."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from nd_b200 import device
-for dtype, kernel in ((np.float64, "auto"), (np.float32, "generic"), (np.float64, "tiled")):
-    shape = (48, 1024, 32, 4)
+for dtype, kernel, shape in ((np.float64, "tiled64", (240, 2048, 32, 4)), (np.float64, "generic", (48, 1024, 32, 4)),
+                            (np.float32, "generic", (48, 1024, 32, 4)), (np.float64, "tiled", (240, 2048, 32, 4)),
+                            (np.float32, "tiled", (240, 2048, 32, 4))):
     cube = device.synth_cube(*shape).to(torch.float64 if dtype == np.float64 else torch.float32)
     plan = device.Plan(shape, (5, 5, 2), (1, 1, 1), 0.25, 0.5, -1, dtype=dtype, kernel=kernel)
     padded = plan.new_padded("cuda"); internal = plan.new_internal_out("cuda")
