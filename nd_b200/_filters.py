@@ -237,7 +237,7 @@ def _sharded(arr, output, r3, f3, sigma, h, n_eff, semantics, kernel, njobs, sha
         slab = arr[tuple(idx)]
         with torch.cuda.device(devices[i]):
             plan = dev.Plan(slab.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype,
-                            kernel='tiled' if whole.is_tiled else 'generic', roles=whole.roles)
+                            kernel=whole.kernel_request, roles=whole.roles)
             if plan.roles != whole.roles or plan.is_tiled != whole.is_tiled:
                 raise RuntimeError('shard %d would use another staged layout than the whole array' % i)
             d_in = torch.from_numpy(slab).to('cuda:%d' % devices[i], non_blocking=True)

@@ -61,7 +61,11 @@ class Plan:
         _lib.check(L.ndnlm_plan_info(self._h, ctypes.byref(info)))
         self.info = info
         self.kernel_name = info.kernel_name.decode()
+        self.is_tiled = info.kernel == _lib.KERNEL_TILED
         self.roles = tuple(int(a) for a in info.role_axis)
+        # the `kernel=` request that reproduces this plan's choice for another shape (the shards of one array)
+        self.kernel_request = ("generic" if not self.is_tiled else
+                               "tiled64" if (dtype == np.float64 and int(info.elem_bytes) == 8) else "tiled")
         self.is_tiled = info.kernel == _lib.KERNEL_TILED
         self.padded_bytes = int(info.padded_bytes)
         self.out_bytes = int(info.out_bytes)
