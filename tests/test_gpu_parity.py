@@ -420,6 +420,45 @@ def test_host_slab_pipeline_pinned_and_neff_error(dev):
                               pipeline=True, slab_rows=48)
 
 
+def test_device_slab_streaming_equals_monolithic_bitwise(dev):
+    """Cubes produced / consumed slab by slab on the device (BASELINE configs[3] / [4] do not fit in HBM with their
+    staged copy and result): `apply_device_streamed` == one monolithic call, bit for bit -- also for a y-shard whose
+    neighbour rows arrive as separate tensors (what the ranks exchange over NCCL in bench.py)."""
+    import torch
+    from nd_b200 import stream
+    a = sar_like((140, 36, 8, 4), seed=16, dtype=np.float32)
+    r, f = (3, 3, 1), (1, 1, 1)
+    whole, _ = run_plan(dev, a, r, f, 0.3, 0.6)
+    d = torch.from_numpy(a).cuda()
+
+    def run(lo, hi, slab_rows, lo_rows, hi_rows):
+        out = torch.full((hi - lo,) + a.shape[1:], float("nan"), device="cuda")
+        seen = []
+
+        def source(s0, s1, dst):
+            dst.copy_(d[lo + s0:lo + s1])
+
+        def sink(s0, s1, res):
+            out[s0:s1] = res
+            seen.append((s0, s1))
+        n = stream.apply_device_streamed(source, sink, hi - lo, a.shape[1:], r, f, 0.3, 0.6, slab_rows=slab_rows,
+                                         lo_rows=lo_rows, hi_rows=hi_rows)
+        assert n == len(seen) and seen[0][0] == 0 and seen[-1][1] == hi - lo
+        return out.cpu().numpy(), n
+
+    out, n = run(0, 140, 40, None, None)
+    assert n >= 3 and np.array_equal(out, whole)
+    out, n = run(0, 140, 1000, None, None)                      # one slab
+    assert n == 1 and np.array_equal(out, whole)
+    halo = 4
+    out, n = run(50, 110, 28, d[50 - halo:50].contiguous(), d[110:110 + halo].contiguous())     # a shard of the cube
+    assert n >= 2 and np.array_equal(out, whole[50:110])
+    out, n = run(0, 60, 28, None, d[60:60 + halo].contiguous())                                  # the first shard
+    assert np.array_equal(out, whole[:60])
+    with pytest.raises(ValueError):
+        run(50, 110, 28, d[50 - 2:50].contiguous(), None)        # neighbour rows of the wrong height
+
+
 # ---- real multi-GPU (skipped on a 1-GPU box) ----------------------------------------------------------
 def test_njobs_two_gpus_equals_one_gpu(dev):
     """The reference's test_parallelized_filter (nd/tests/test_filters_common.py:54-60) with njobs = GPUs:
