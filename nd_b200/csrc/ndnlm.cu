@@ -584,7 +584,7 @@ static encode_tiled_fn get_encode_fn() {
 extern "C" size_t ndnlm_scratch_bytes(const ndnlm_plan_t* pl) {
     if (!pl || !pl->boxmean) return 0;
     const DevParams& P = pl->P;
-    return size_t(P.n[0] + 2 * P.rad[0]) * P.n[1] * P.n[2] * P.nv4 * sizeof(float4);
+    return boxmean_scratch_rows(P) * P.n[1] * P.n[2] * P.nv4 * sizeof(float4);
 }
 
 extern "C" int ndnlm_run(const ndnlm_plan_t* pl, const void* padded, void* out_internal, int32_t* err_flag, void* stream) {
@@ -600,8 +600,9 @@ extern "C" int ndnlm_run_scratch(const ndnlm_plan_t* pl, const void* padded, voi
     if (pl->kernel == NDNLM_KERNEL_TILED && pl->boxmean) {
         float4* inter = (float4*)scratch;
         if (!inter) CUDA_TRY(cudaMallocAsync((void**)&inter, ndnlm_scratch_bytes(pl), st));
-        cudaError_t e = boxmean_run(P, (const float4*)padded, (float4*)out_internal, inter, st);
-        g_launches += 2;
+        int nl = 0;
+        cudaError_t e = boxmean_run(P, (const float4*)padded, (float4*)out_internal, inter, st, &nl);
+        g_launches += nl;
         if (!scratch) cudaFreeAsync(inter, st);
         if (e != cudaSuccess) return fail(NDNLM_ECUDA, "box-mean kernels failed to launch: %s", cudaGetErrorString(e));
     } else if (pl->kernel == NDNLM_KERNEL_TILED) {

@@ -12,8 +12,9 @@
 //   boxmean_w_kernel   one thread per (X, R) element: marches along W with a register ring of 2 r_W + 1 rows,
 //                      fully coalesced, and scales by 1 / (K + 1).
 //
-// Both are one coalesced read + one coalesced write of the cube (an L2-resident slab variant was considered and
-// dropped: a slab small enough for the 126 MB L2 -- a cfg3 row is 2 MB -- has too few rows to fill 148 SMs).
+// Both are one coalesced read + one coalesced write of the cube.  (Running the pair slab by slab so that the
+// intermediate stays in the 126 MB L2 -- NDNLM_BOXMEAN_SLAB=rows, a tuning aid -- is slower at every slab height: a
+// slab small enough for L2, a cfg3 row being 2 MB, has too few rows to fill 148 SMs)
 // The reference accumulates `weighted_sum` in float32 in (y, x, t) loop order; a separable float32 sum differs
 // from it by its own rounding noise (~1e-7 scaled, tests allow 1e-5).
 #pragma once
@@ -227,52 +228,82 @@ inline bool boxmean_supported(const DevParams& P) {
 
 
 // padded: staged cube [q][pd0][pd2][pd1] float4; out: [q][n0][n2][n1] float4; inter: (n0 + 2 rW) n1 n2 nv4 float4
-inline cudaError_t boxmean_run(const DevParams& P, const float4* padded, float4* out, float4* inter, cudaStream_t st) {
+template <int DUMMY = 0>
+inline cudaError_t boxmean_launch_xr(const BoxParams& B, int rX, const float4* padded, float4* inter, cudaStream_t st) {
+    const long long warps = (long long)B.nv4 * B.w_count * B.nwr * B.nseg;
+    const unsigned grid = unsigned((warps * 32 + 127) / 128);
+    switch (boxmean_ring_for(rX)) {
+        case 3: boxmean_xr_kernel<3><<<grid, 128, 0, st>>>(B, padded, inter); break;
+        case 7: boxmean_xr_kernel<7><<<grid, 128, 0, st>>>(B, padded, inter); break;
+        case 11: boxmean_xr_kernel<11><<<grid, 128, 0, st>>>(B, padded, inter); break;
+        case 15: boxmean_xr_kernel<15><<<grid, 128, 0, st>>>(B, padded, inter); break;
+        default: boxmean_xr_kernel<21><<<grid, 128, 0, st>>>(B, padded, inter); break;
+    }
+    return cudaGetLastError();
+}
+template <int DUMMY = 0>
+inline cudaError_t boxmean_launch_w(const BoxParams& B, int rW, const float4* inter, float4* out, cudaStream_t st) {
+    const long long plane = (long long)B.n[1] * B.n[2];
+    const unsigned grid = unsigned((plane * B.nwseg * B.nv4 + 255) / 256);
+    switch (boxmean_ring_for(rW)) {
+        case 3: boxmean_w_kernel<3><<<grid, 256, 0, st>>>(B, inter, out); break;
+        case 7: boxmean_w_kernel<7><<<grid, 256, 0, st>>>(B, inter, out); break;
+        case 11: boxmean_w_kernel<11><<<grid, 256, 0, st>>>(B, inter, out); break;
+        case 15: boxmean_w_kernel<15><<<grid, 256, 0, st>>>(B, inter, out); break;
+        default: boxmean_w_kernel<21><<<grid, 256, 0, st>>>(B, inter, out); break;
+    }
+    return cudaGetLastError();
+}
+
+// Rows of W that one (xr, w) kernel pair handles.  0 = the whole cube in one pair.  A slab whose intermediate
+// ((slab + 2 r_W) rows) stays in the 126 MB L2 lets the W pass read it from L2 instead of DRAM.
+inline int boxmean_slab_rows(const DevParams& P) {
+    const char* env = getenv("NDNLM_BOXMEAN_SLAB");
+    if (env) return atoi(env);
+    return 0;
+}
+inline size_t boxmean_scratch_rows(const DevParams& P) {
+    const int slab = boxmean_slab_rows(P);
+    return size_t((slab > 0 && slab < P.n[0]) ? slab : P.n[0]) + 2 * size_t(P.rad[0]);
+}
+
+// padded: staged cube [q][pd0][pd2][pd1] float4; out: [q][n0][n2][n1] float4; inter: boxmean_scratch_rows x n1 n2 nv4 float4
+inline cudaError_t boxmean_run(const DevParams& P, const float4* padded, float4* out, float4* inter, cudaStream_t st, int* launches) {
     BoxParams B;
     for (int k = 0; k < 3; ++k) { B.n[k] = P.n[k]; B.rad[k] = P.rad[k]; B.pad[k] = P.pad[k]; B.pd[k] = P.pd[k]; }
     B.nv4 = P.nv4;
-    B.w_first = P.pad[0] - P.rad[0];
-    B.w_count = P.n[0] + 2 * P.rad[0];
-    B.out_first = 0;
-    B.out_count = P.n[0];
     const double K1 = double(2 * P.rad[0] + 1) * (2 * P.rad[1] + 1) * (2 * P.rad[2] + 1);
     B.scale = float(1.0 / K1);
     B.nwr = (P.n[1] + (32 - 2 * P.rad[1]) - 1) / (32 - 2 * P.rad[1]);
-    // enough threads to fill the machine: ~64 K warps in flight at most, segments of at least 4 ring lengths
-    const long long rows_warps = (long long)B.nv4 * B.w_count * B.nwr;
-    int nseg = int((8192 + rows_warps - 1) / rows_warps);
-    const int min_seg = 4 * (2 * P.rad[2] + 1);
-    nseg = nseg < 1 ? 1 : nseg;
-    B.seg_len = (P.n[2] + nseg - 1) / nseg;
-    if (B.seg_len < min_seg) B.seg_len = min_seg;
-    B.nseg = (P.n[2] + B.seg_len - 1) / B.seg_len;
-    const long long warps = rows_warps * B.nseg;
-    const unsigned grid_xr = unsigned((warps * 32 + 127) / 128);
-    switch (boxmean_ring_for(P.rad[2])) {
-        case 3: boxmean_xr_kernel<3><<<grid_xr, 128, 0, st>>>(B, padded, inter); break;
-        case 7: boxmean_xr_kernel<7><<<grid_xr, 128, 0, st>>>(B, padded, inter); break;
-        case 11: boxmean_xr_kernel<11><<<grid_xr, 128, 0, st>>>(B, padded, inter); break;
-        case 15: boxmean_xr_kernel<15><<<grid_xr, 128, 0, st>>>(B, padded, inter); break;
-        default: boxmean_xr_kernel<21><<<grid_xr, 128, 0, st>>>(B, padded, inter); break;
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    int slab = boxmean_slab_rows(P);
+    if (slab <= 0 || slab > P.n[0]) slab = P.n[0];
     const long long plane = (long long)P.n[1] * P.n[2];
-    int nwseg = int((262144 + plane * B.nv4 - 1) / (plane * B.nv4));
-    nwseg = nwseg < 1 ? 1 : nwseg;
-    B.w_seg = (P.n[0] + nwseg - 1) / nwseg;
-    const int min_wseg = 4 * (2 * P.rad[0] + 1);
-    if (B.w_seg < min_wseg) B.w_seg = min_wseg;
-    B.nwseg = (P.n[0] + B.w_seg - 1) / B.w_seg;
-    const unsigned grid_w = unsigned((plane * B.nwseg * B.nv4 + 255) / 256);
-    switch (boxmean_ring_for(P.rad[0])) {
-        case 3: boxmean_w_kernel<3><<<grid_w, 256, 0, st>>>(B, inter, out); break;
-        case 7: boxmean_w_kernel<7><<<grid_w, 256, 0, st>>>(B, inter, out); break;
-        case 11: boxmean_w_kernel<11><<<grid_w, 256, 0, st>>>(B, inter, out); break;
-        case 15: boxmean_w_kernel<15><<<grid_w, 256, 0, st>>>(B, inter, out); break;
-        default: boxmean_w_kernel<21><<<grid_w, 256, 0, st>>>(B, inter, out); break;
+    for (int s0 = 0; s0 < P.n[0]; s0 += slab) {
+        B.out_first = s0;
+        B.out_count = (P.n[0] - s0 < slab) ? P.n[0] - s0 : slab;
+        B.w_first = s0 + P.pad[0] - P.rad[0];
+        B.w_count = B.out_count + 2 * P.rad[0];
+        // enough warps to fill the machine (~8 K), X segments of at least 4 ring lengths
+        const long long rows_warps = (long long)B.nv4 * B.w_count * B.nwr;
+        int nseg = int((8192 + rows_warps - 1) / rows_warps);
+        const int min_seg = 4 * (2 * P.rad[2] + 1);
+        nseg = nseg < 1 ? 1 : nseg;
+        B.seg_len = (P.n[2] + nseg - 1) / nseg;
+        if (B.seg_len < min_seg) B.seg_len = min_seg;
+        B.nseg = (P.n[2] + B.seg_len - 1) / B.seg_len;
+        cudaError_t e = boxmean_launch_xr(B, P.rad[2], padded, inter, st);
+        if (e != cudaSuccess) return e;
+        int nwseg = int((262144 + plane * B.nv4 - 1) / (plane * B.nv4));
+        nwseg = nwseg < 1 ? 1 : nwseg;
+        B.w_seg = (B.out_count + nwseg - 1) / nwseg;
+        const int min_wseg = 4 * (2 * P.rad[0] + 1);
+        if (B.w_seg < min_wseg) B.w_seg = min_wseg;
+        B.nwseg = (B.out_count + B.w_seg - 1) / B.w_seg;
+        e = boxmean_launch_w(B, P.rad[0], inter, out, st);
+        if (e != cudaSuccess) return e;
+        *launches += 2;
     }
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 
 }  // namespace ndnlm
