@@ -4,6 +4,7 @@ meaning and error behaviour, on host NumPy arrays -- but the arithmetic runs on 
 libndnlm.so (include/ndnlm.h).  There is no CPU fallback: without a CUDA device or without the
 built library this raises.
 """
+import logging
 import math
 
 import numpy as np
@@ -89,6 +90,12 @@ def _pixelwise_nlmeans_3d(arr, output, r, f, sigma, h, n_eff=-1, *, semantics=No
         _stream.apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff, semantics=semantics, kernel=kernel,
                                      slab_rows=slab_rows)
         return
+    if pipeline:
+        # not an error, but worth knowing when a large array takes the slow road
+        logging.getLogger('nd_b200').info(
+            'host array of shape %s (strides %s) is copied to the GPU in one piece: the slab pipeline needs a dense '
+            'layout shared by input and output and at least %d rows along axis 0', arr.shape, arr.strides,
+            max(128, 8 * (r3[0] + f3[0])))
 
     plan = dev.Plan(arr.shape, r3, f3, sigma, h, n_eff, semantics=semantics, dtype=arr.dtype, kernel=kernel)
     d_in = torch.from_numpy(arr).cuda()

@@ -101,7 +101,8 @@ def map_over_tiles(files, fn, args=(), kwargs={}, path=None, suffix='', merge=Tr
 
 
 def sort_into_array(datasets, dims=None):
-    """An object array laid out like the tile grid (reference nd/tiling.py:210-240)."""
+    """An object array laid out like the tile grid (reference nd/tiling.py:210-240).  `dims` is accepted and ignored
+    exactly as in the reference, whose first statement overwrites it with the dims of the first dataset (:214)."""
     dims = get_dims(datasets[0])
     initials = {dim: np.unique([d.coords[dim][0] for d in datasets]) for dim in dims}
     grid = np.empty(tuple(len(initials[dim]) for dim in dims), dtype=object)
