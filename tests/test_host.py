@@ -66,12 +66,24 @@ def test_algorithmic_flops_match_baseline_table(shape, r, f, n_eff, F):
 
 
 def test_plan_kernel_selection():
-    assert device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64).kernel_name == "nlm_generic<double>"
+    # float64 data: the float64 instantiation of the tiled kernel where one exists (32-byte voxels), else generic
+    pd = device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64)
+    assert pd.is_tiled and "double" in pd.kernel_name and pd.kernel_request == "tiled64"
+    assert pd.padded_bytes == (40 + 6) * (50 + 6) * (30 + 4) * 32 and pd.out_bytes == 40 * 50 * 30 * 32
+    assert device.Plan((40, 50, 30, 4), (2, 2, 1), (2, 2, 2), 1, 1, dtype=np.float64).kernel_name == "nlm_generic<double>"
+    assert device.Plan((40, 50, 30, 6), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64).kernel_name == "nlm_generic<double>"
+    assert device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64, kernel="tiled64").is_tiled
+    with pytest.raises(ValueError):
+        device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float32, kernel="tiled64")
+    pb = device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, semantics="reference_compiled")
+    assert "boxmean" in pb.kernel_name and pb.scratch_bytes == (40 + 4) * 50 * 30 * 16 and pb.kernel_request == "tiled"
+    assert device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, n_eff=5, semantics="reference_compiled").kernel_name \
+        == "nlm_generic<float>[zero_dist]"
     assert "zero_dist" in device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, semantics="reference_compiled").kernel_name
     assert device.Plan((40, 50, 30, 4), (2, 2, 1), (0, 0, 0), 1, 1, semantics="reference_compiled").is_tiled
     assert device.Plan((1, 206, 500, 4), (0, 3, 3), (0, 1, 1), 1, 1).is_tiled
     assert not device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, kernel="generic").is_tiled
-    # float64 data: generic float64 kernel by default, the fp32 tiled kernel only on explicit request
+    # float64 data on the fp32 tiled kernel only on explicit request
     p64 = device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64, kernel="tiled")
     assert p64.is_tiled and p64.padded_bytes == (40 + 6) * (50 + 6) * (30 + 4) * 16
     with pytest.raises(ValueError):                                  # V > 8 has no tiled instantiation
