@@ -446,15 +446,17 @@ class NLMeansFilter(Filter):
         ndim = arrays[0].ndim
         if ndim > 3 or ndim < len(self.r) or not np.any(self.r) or len(self.r) == 0:
             return False
-        pad_before = np.zeros(3 - ndim, dtype=self.r.dtype)
-        pad_after = np.zeros(ndim - len(self.r), dtype=self.r.dtype)
-        r = np.concatenate([pad_before, self.r, pad_after])
-        f = np.concatenate([pad_before, self.f, pad_after])
-        njobs, shard_axis = self._njobs_and_shard_axis(len(pad_before))
+        # Missing axes are singletons.  `_filter` puts them in front (nd/filters.py:451-460); here they go BEHIND the
+        # data axes, which is the same filter (a singleton axis carries no neighbours) but leaves the first data
+        # axis -- 'y' of a 2-D image -- as axis 0, the axis the slab pipeline and the GPU shards cut along.
+        pad_after = np.zeros(3 - len(self.r), dtype=self.r.dtype)
+        r = np.concatenate([self.r, pad_after])
+        f = np.concatenate([self.f, pad_after])
+        njobs, shard_axis = self._njobs_and_shard_axis(0)
         if shard_axis not in (None, 0):
             return False
-        a3 = [a.reshape((1,) * (3 - ndim) + a.shape) for a in arrays]
-        o3 = [o.reshape((1,) * (3 - ndim) + o.shape) for o in outputs]
+        a3 = [a.reshape(a.shape + (1,) * (3 - ndim)) for a in arrays]
+        o3 = [o.reshape(o.shape + (1,) * (3 - ndim)) for o in outputs]
         if r[0] == 0 and f[0] == 0 and njobs > 1 and a3[0].shape[0] < njobs:
             return False                      # a short free leading axis: shard along a filtered one (block path)
         return nlmeans_variables(a3, o3, r, f, self.sigma, self.h, self.n_eff, semantics=self.semantics,

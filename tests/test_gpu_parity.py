@@ -498,6 +498,16 @@ def test_dataset_apply_streams_the_variables_and_equals_the_block_path(dev, dtyp
         assert out_fast[v].dims == ds[v].dims and out_fast[v].values.dtype == ds[v].values.dtype
     assert out_fast['mask'].values is not ds['mask'].values         # untouched variables are copies, like deep copy
     assert out_fast['C11'].values.std() < ds['C11'].values.std()
+    # a 2-D image (the reference's most common use): streamed along 'y' too; the block path lays the axes out as
+    # (1, y, x), the streamed one as (y, x, 1) -- the same filter, another summation order
+    ds2 = ds.isel(time=0)
+    kw2 = dict(dims=('y', 'x'), r=(2, 3), sigma=1, h=1)
+    fast2, slow2 = NLMeansFilter(**kw2), NLMeansFilter(**kw2)
+    slow2._filter_variables = None
+    o_fast, o_slow = fast2.apply(ds2), slow2.apply(ds2)
+    for v in ('C11', 'C22', 'C12__re', 'C12__im'):
+        assert o_fast[v].dims == ('y', 'x') and scaled_err(o_fast[v].values[..., None], o_slow[v].values[..., None]) < (
+            1e-12 if dtype == np.float64 else 1e-6), v
     import torch
     if torch.cuda.device_count() >= 2:
         out_two = NLMeansFilter(**kw).apply(ds, njobs=2)
