@@ -113,7 +113,8 @@ def test_float64_matches_oracle(dev, c_oracle, shape, r, f):
 
 
 @pytest.mark.parametrize("shape,r,f", [CASES[0], CASES[1], CASES[2], CASES[3], CASES[4], CASES[5], CASES[6], CASES[7],
-                                       CASES[8], CASES[9], ((40, 70, 33, 4), (5, 5, 2), (1, 1, 1))])
+                                       CASES[8], CASES[9], CASES[10], CASES[14], ((1, 24, 40, 4), (0, 4, 4), (0, 2, 2)),
+                                       ((40, 70, 33, 4), (5, 5, 2), (1, 1, 1))])
 def test_float64_tiled_kernel_matches_oracle_to_1e12(dev, c_oracle, shape, r, f):
     """float64 data (every fixture of the reference, nd/testing.py:68-69) runs on the float64 instantiations of the
     tiled kernel: the reference's own float64 arithmetic (nd/_filters.pyx:320-321), <= 1e-12 from the oracle."""

@@ -70,7 +70,8 @@ def test_plan_kernel_selection():
     pd = device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64)
     assert pd.is_tiled and "double" in pd.kernel_name and pd.kernel_request == "tiled64"
     assert pd.padded_bytes == (40 + 6) * (50 + 6) * (30 + 4) * 32 and pd.out_bytes == 40 * 50 * 30 * 32
-    assert device.Plan((40, 50, 30, 4), (2, 2, 1), (2, 2, 2), 1, 1, dtype=np.float64).kernel_name == "nlm_generic<double>"
+    assert "double" in device.Plan((40, 50, 30, 4), (2, 2, 1), (2, 2, 2), 1, 1, dtype=np.float64).kernel_name   # f = 2 too
+    assert device.Plan((40, 50, 30, 4), (2, 2, 1), (3, 3, 3), 1, 1, dtype=np.float64).kernel_name == "nlm_generic<double>"
     assert device.Plan((40, 50, 30, 6), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64).kernel_name == "nlm_generic<double>"
     assert device.Plan((40, 50, 30, 4), (2, 2, 1), (1, 1, 1), 1, 1, dtype=np.float64, kernel="tiled64").is_tiled
     with pytest.raises(ValueError):
