@@ -252,3 +252,34 @@ def test_dataset_standin_roundtrip():
     c = ds.copy(deep=True)
     c['C11'].values[0, 0, 0] += 1
     assert not ds.equals(c)
+
+
+# ---- round 2: host-side pieces of the streaming layer (no GPU needed) ----------------------------------
+def test_parallel_staging_copy_and_variable_list():
+    import torch
+    from nd_b200 import stream
+    a = torch.arange(3 * 70 * 1024 * 64, dtype=torch.float32).reshape(3 * 70, 1024, 64)      # ~55 MB: below the split size
+    b = torch.empty_like(a)
+    stream.par_copy(b, a)
+    assert torch.equal(a, b)
+    big = torch.ones(5, 1 << 22, dtype=torch.float32)                                           # 80 MB: split over threads
+    out = torch.zeros_like(big)
+    stream.par_copy(out, big)
+    assert torch.equal(out, big)
+    v = stream._VarList([np.full((4, 5, 6), k, np.float32) for k in range(3)])
+    assert v[(2,)].shape == (4, 5, 6) and float(v[(2,)][0, 0, 0]) == 2.0 and not v.is_pinned()
+
+
+def test_nlmeans_variables_declines_what_it_cannot_stream():
+    from nd_b200._filters import nlmeans_variables
+    u = lambda *x: np.array(x, dtype=np.uint32)
+    a = [np.zeros((64, 20, 6), np.float32) for _ in range(3)]
+    o = [np.empty_like(x) for x in a]
+    assert nlmeans_variables(a[:2] + [a[2][:, ::2]], o[:2] + [o[2][:, ::2]], u(2, 2, 1), u(1, 1, 1), 1, 1) is False   # not contiguous
+    assert nlmeans_variables(a, o[:2], u(2, 2, 1), u(1, 1, 1), 1, 1) is False                                      # one output missing
+    assert nlmeans_variables([x[:10] for x in a], [x[:10] for x in o], u(2, 2, 1), u(1, 1, 1), 1, 1) is False      # too few rows
+    assert nlmeans_variables([x.astype(np.int16) for x in a], o, u(2, 2, 1), u(1, 1, 1), 1, 1) is False
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            nlmeans_variables(a, o, u(2, 2, 1), u(1, 1, 1), 1, 1)
