@@ -73,6 +73,7 @@ static inline unsigned blocks_for(long long total, int threads) { return unsigne
 
 struct TiledInst {
     int elem;           // bytes per element of the staged cube the kernel computes in: 4 (float) or 8 (double)
+    bool half;          // the last variable group carries at most two variables (V = 5, 6): its upper lanes are skipped
     int nv4, fw, fx, fr, L, nwarps, ch;
     bool neff;
     size_t exch_bytes;
@@ -87,6 +88,9 @@ struct TiledInst {
 #define TILED_INST64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                      \
     extern template cudaError_t launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF>(                       \
         const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
+#define TILED_INSTH(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                       \
+    extern template cudaError_t launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF, true>(                  \
+        const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
 #include "instances_g0.inc"
 #include "instances_g1.inc"
 #include "instances_g2.inc"
@@ -95,16 +99,23 @@ struct TiledInst {
 #include "instances_g5.inc"
 #undef TILED_INST
 #undef TILED_INST64
+#undef TILED_INSTH
 
+#define TILED_INSTH(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                \
+    {                                                                                                \
+        4, true, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+            launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF, true>,                             \
+            "nlm_tiled<nv4=" #NV4 "(half),f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
+    },
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
     {                                                                                                \
-        4, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+        4, false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
             launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF>,                                   \
             "nlm_tiled<nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
     },
 #define TILED_INST64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                               \
     {                                                                                                \
-        8, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<double, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+        8, false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<double, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
             launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF>,                                  \
             "nlm_tiled<double,nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
     },
@@ -120,6 +131,7 @@ static const TiledInst g_tiled[] = {
 };
 #undef TILED_INST
 #undef TILED_INST64
+#undef TILED_INSTH
 static const int g_ntiled = int(sizeof(g_tiled) / sizeof(g_tiled[0]));
 
 // ------------------------------------------------------------------------------------------
@@ -158,6 +170,7 @@ static int largest_divisor_leq(int n, int cap) {
 static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti, int elem) {
     DevParams& P = pl->P;
     if (ti.elem != elem || ti.nv4 != P.nv4) return false;
+    if (ti.half && P.V > 4 * ti.nv4 - 2) return false;
     if (ti.fw != P.fr[0] || ti.fr != P.fr[1] || ti.fx != P.fr[2]) return false;
     if (ti.neff != (pl->n_eff >= 0)) return false;
     const int txw = 32 - 2 * ti.fx;

@@ -4,6 +4,9 @@
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
     template cudaError_t launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF>(                       \
         const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
+#define TILED_INSTH(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                \
+    template cudaError_t launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF, true>(                 \
+        const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
 #define TILED_INST64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                               \
     template cudaError_t launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF>(                      \
         const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);

@@ -251,7 +251,10 @@ struct TiledCfg {
     static constexpr size_t EXCH_BYTES = FW > 0 ? size_t(CH) * NWARPS * (L / 2) * 32 * sizeof(typename Elem<T>::P2) : 0;
 };
 
-template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
+// HALF: the last variable group holds at most two real variables (V = 5 or 6 of 8): its upper two lanes are zero
+// padding, and every load, difference, square and accumulation on them is skipped (64-bit instead of 128-bit
+// shared-memory loads, 3 instead of 4 packed operations per voxel pair, a quarter fewer registers for that group).
+template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF, bool HALF = false>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                  const typename Elem<T>::V4* __restrict__ padded, typename Elem<T>::V4* __restrict__ out,
@@ -356,9 +359,15 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int gr = r0 + lr0 + e;
-                c[q][e] = (inb && gr < P.pd[1])
-                              ? padded[((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr]
-                              : mk4(T(0), T(0), T(0), T(0));
+                const V4* src = padded + ((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr;
+                if (!(inb && gr < P.pd[1])) {
+                    c[q][e] = mk4(T(0), T(0), T(0), T(0));
+                } else if (HALF && q == NV4 - 1) {
+                    const P2 t = *reinterpret_cast<const P2*>(src);
+                    c[q][e] = mk4(t.x, t.y, T(0), T(0));
+                } else {
+                    c[q][e] = *src;
+                }
             }
     }
 
@@ -412,7 +421,14 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
 #pragma unroll
         for (int k = 0; k < WNJ; ++k) {
 #pragma unroll
-            for (int q = 0; q < NV4; ++q) n[q][k] = nb[size_t(q) * plane + k];
+            for (int q = 0; q < NV4; ++q) {
+                if (HALF && q == NV4 - 1) {
+                    const P2 t = *reinterpret_cast<const P2*>(nb + size_t(q) * plane + k);
+                    n[q][k] = mk4(t.x, t.y, T(0), T(0));
+                } else {
+                    n[q][k] = nb[size_t(q) * plane + k];
+                }
+            }
         }
 
         auto weigh = [&](const P2 (&D)[L / 2], const int j) {
@@ -431,9 +447,11 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
 #pragma unroll
                 for (int q = 0; q < NV4; ++q) {
                     acc_lo[q][o] = pfma(w0b, lo2(n[q][o + FR + j]), acc_lo[q][o]);
-                    acc_hi[q][o] = pfma(w0b, hi2(n[q][o + FR + j]), acc_hi[q][o]);
                     acc_lo[q][o + 1] = pfma(w1b, lo2(n[q][o + 1 + FR + j]), acc_lo[q][o + 1]);
-                    acc_hi[q][o + 1] = pfma(w1b, hi2(n[q][o + 1 + FR + j]), acc_hi[q][o + 1]);
+                    if (!(HALF && q == NV4 - 1)) {
+                        acc_hi[q][o] = pfma(w0b, hi2(n[q][o + FR + j]), acc_hi[q][o]);
+                        acc_hi[q][o + 1] = pfma(w1b, hi2(n[q][o + 1 + FR + j]), acc_hi[q][o + 1]);
+                    }
                 }
             }
         };
@@ -451,9 +469,11 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
 #pragma unroll
                 for (int q = 0; q < NV4; ++q) {
                     const P2 d0 = padd(lo2(c[q][e]), pneg(lo2(n[q][e + j])));
-                    const P2 d1 = padd(hi2(c[q][e]), pneg(hi2(n[q][e + j])));
                     sq = (q == 0) ? pmul(d0, d0) : pfma(d0, d0, sq);
-                    sq = pfma(d1, d1, sq);
+                    if (!(HALF && q == NV4 - 1)) {
+                        const P2 d1 = padd(hi2(c[q][e]), pneg(hi2(n[q][e + j])));
+                        sq = pfma(d1, d1, sq);
+                    }
                 }
                 s[e] = sq.x + sq.y;
             }
@@ -628,8 +648,13 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 // weighted_sum has the data type in the reference and is rounded after the self term (:419)
                 res.x = T(double(T(double(acc_lo[q][o].x) + ws * double(cc.x))) / tot);
                 res.y = T(double(T(double(acc_lo[q][o].y) + ws * double(cc.y))) / tot);
-                res.z = T(double(T(double(acc_hi[q][o].x) + ws * double(cc.z))) / tot);
-                res.w = T(double(T(double(acc_hi[q][o].y) + ws * double(cc.w))) / tot);
+                if (HALF && q == NV4 - 1) {
+                    res.z = T(0);
+                    res.w = T(0);
+                } else {
+                    res.z = T(double(T(double(acc_hi[q][o].x) + ws * double(cc.z))) / tot);
+                    res.w = T(double(T(double(acc_hi[q][o].y) + ws * double(cc.w))) / tot);
+                }
                 po[q * oplane + o] = res;
             }
         }

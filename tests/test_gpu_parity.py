@@ -82,6 +82,9 @@ CASES = [
     ((13, 31, 8, 4), (7, 7, 2), (2, 2, 2)),        # cfg4 parameters (tiled f = 2, several W passes)
     ((14, 29, 9, 6), (10, 10, 3), (2, 2, 2)),      # cfg5 parameters (V = 6, f = 2: two variable groups, one W offset per pass)
     ((1, 24, 40, 6), (0, 4, 4), (0, 2, 2)),        # 2-D, V = 6, f = 2
+    ((10, 33, 8, 5), (2, 2, 1), (1, 1, 1)),        # V = 5: the second variable group is a "half" group (one real variable)
+    ((10, 33, 8, 7), (2, 2, 1), (1, 1, 1)),        # V = 7: full second group
+    ((16, 40, 9, 6), (5, 5, 2), (1, 1, 1)),        # V = 6 with the cfg3 radii (12-warp half-group instantiation)
 ]
 
 
@@ -92,6 +95,15 @@ def test_matches_oracle_float32(dev, c_oracle, shape, r, f):
     out, plan = run_plan(dev, a, r, f, 0.3, 0.6)
     assert scaled_err(out, ref) < TOL32, plan.kernel_name
     assert not np.isnan(out).any()
+
+
+def test_half_variable_group_instantiations_are_selected(dev):
+    """V = 5, 6: the second float4 group carries at most two variables; its upper lanes are skipped (HALF
+    instantiations).  V = 7, 8 and V <= 4 must not take them."""
+    for V, half in ((4, False), (5, True), (6, True), (7, False), (8, False)):
+        for r, f in (((2, 2, 1), (1, 1, 1)), ((3, 3, 1), (2, 2, 2)), ((0, 3, 3), (0, 1, 1))):
+            plan = dev.Plan((12, 40, 9, V), r, f, 0.3, 0.6)
+            assert plan.is_tiled and ("(half)" in plan.kernel_name) == half, (V, r, plan.kernel_name)
 
 
 @pytest.mark.parametrize("shape,r,f", CASES[:3] + CASES[4:7])
