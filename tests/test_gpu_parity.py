@@ -199,10 +199,10 @@ def test_reference_compiled_neff_stays_on_the_generic_kernel(dev, c_oracle):
 
 def test_neff(dev, c_oracle):
     a = sar_like((10, 16, 7, 4), seed=5, dtype=np.float32)
-    for r, f in (((2, 2, 1), (1, 1, 1)), ((0, 2, 2), (0, 1, 1))):
+    for r, f in (((2, 2, 1), (1, 1, 1)), ((0, 2, 2), (0, 1, 1)), ((2, 2, 1), (2, 2, 2)), ((0, 3, 2), (0, 2, 2))):
         ref = c_oracle.nlmeans(a, r, f, 0.3, 1.5, n_eff=6.0)
         out, plan = run_plan(dev, a, r, f, 0.3, 1.5, n_eff=6.0)
-        assert scaled_err(out, ref) < TOL32, plan.kernel_name
+        assert plan.is_tiled and scaled_err(out, ref) < TOL32, plan.kernel_name
 
 
 def test_neff_no_solution_raises_value_error(dev):
