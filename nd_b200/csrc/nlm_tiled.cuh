@@ -359,14 +359,20 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int gr = r0 + lr0 + e;
-                const V4* src = padded + ((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr;
-                if (!(inb && gr < P.pd[1])) {
-                    c[q][e] = mk4(T(0), T(0), T(0), T(0));
-                } else if (HALF && q == NV4 - 1) {
-                    const P2 t = *reinterpret_cast<const P2*>(src);
-                    c[q][e] = mk4(t.x, t.y, T(0), T(0));
+                if constexpr (HALF) {
+                    const V4* src = padded + ((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr;
+                    if (!(inb && gr < P.pd[1])) {
+                        c[q][e] = mk4(T(0), T(0), T(0), T(0));
+                    } else if (q == NV4 - 1) {
+                        const P2 t = *reinterpret_cast<const P2*>(src);
+                        c[q][e] = mk4(t.x, t.y, T(0), T(0));
+                    } else {
+                        c[q][e] = *src;
+                    }
                 } else {
-                    c[q][e] = *src;
+                    c[q][e] = (inb && gr < P.pd[1])
+                                  ? padded[((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr]
+                                  : mk4(T(0), T(0), T(0), T(0));
                 }
             }
     }
@@ -422,9 +428,13 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         for (int k = 0; k < WNJ; ++k) {
 #pragma unroll
             for (int q = 0; q < NV4; ++q) {
-                if (HALF && q == NV4 - 1) {
-                    const P2 t = *reinterpret_cast<const P2*>(nb + size_t(q) * plane + k);
-                    n[q][k] = mk4(t.x, t.y, T(0), T(0));
+                if constexpr (HALF) {
+                    if (q == NV4 - 1) {
+                        const P2 t = *reinterpret_cast<const P2*>(nb + size_t(q) * plane + k);
+                        n[q][k] = mk4(t.x, t.y, T(0), T(0));
+                    } else {
+                        n[q][k] = nb[size_t(q) * plane + k];
+                    }
                 } else {
                     n[q][k] = nb[size_t(q) * plane + k];
                 }
@@ -446,10 +456,17 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 const P2 w0b = mk2(w0_, w0_), w1b = mk2(w1_, w1_);
 #pragma unroll
                 for (int q = 0; q < NV4; ++q) {
-                    acc_lo[q][o] = pfma(w0b, lo2(n[q][o + FR + j]), acc_lo[q][o]);
-                    acc_lo[q][o + 1] = pfma(w1b, lo2(n[q][o + 1 + FR + j]), acc_lo[q][o + 1]);
-                    if (!(HALF && q == NV4 - 1)) {
+                    if constexpr (HALF) {
+                        acc_lo[q][o] = pfma(w0b, lo2(n[q][o + FR + j]), acc_lo[q][o]);
+                        acc_lo[q][o + 1] = pfma(w1b, lo2(n[q][o + 1 + FR + j]), acc_lo[q][o + 1]);
+                        if (q != NV4 - 1) {
+                            acc_hi[q][o] = pfma(w0b, hi2(n[q][o + FR + j]), acc_hi[q][o]);
+                            acc_hi[q][o + 1] = pfma(w1b, hi2(n[q][o + 1 + FR + j]), acc_hi[q][o + 1]);
+                        }
+                    } else {
+                        acc_lo[q][o] = pfma(w0b, lo2(n[q][o + FR + j]), acc_lo[q][o]);
                         acc_hi[q][o] = pfma(w0b, hi2(n[q][o + FR + j]), acc_hi[q][o]);
+                        acc_lo[q][o + 1] = pfma(w1b, lo2(n[q][o + 1 + FR + j]), acc_lo[q][o + 1]);
                         acc_hi[q][o + 1] = pfma(w1b, hi2(n[q][o + 1 + FR + j]), acc_hi[q][o + 1]);
                     }
                 }
@@ -468,10 +485,17 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 P2 sq;
 #pragma unroll
                 for (int q = 0; q < NV4; ++q) {
-                    const P2 d0 = padd(lo2(c[q][e]), pneg(lo2(n[q][e + j])));
-                    sq = (q == 0) ? pmul(d0, d0) : pfma(d0, d0, sq);
-                    if (!(HALF && q == NV4 - 1)) {
+                    if constexpr (HALF) {
+                        const P2 d0 = padd(lo2(c[q][e]), pneg(lo2(n[q][e + j])));
+                        sq = (q == 0) ? pmul(d0, d0) : pfma(d0, d0, sq);
+                        if (q != NV4 - 1) {
+                            const P2 d1 = padd(hi2(c[q][e]), pneg(hi2(n[q][e + j])));
+                            sq = pfma(d1, d1, sq);
+                        }
+                    } else {
+                        const P2 d0 = padd(lo2(c[q][e]), pneg(lo2(n[q][e + j])));
                         const P2 d1 = padd(hi2(c[q][e]), pneg(hi2(n[q][e + j])));
+                        sq = (q == 0) ? pmul(d0, d0) : pfma(d0, d0, sq);
                         sq = pfma(d1, d1, sq);
                     }
                 }
@@ -648,9 +672,14 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 // weighted_sum has the data type in the reference and is rounded after the self term (:419)
                 res.x = T(double(T(double(acc_lo[q][o].x) + ws * double(cc.x))) / tot);
                 res.y = T(double(T(double(acc_lo[q][o].y) + ws * double(cc.y))) / tot);
-                if (HALF && q == NV4 - 1) {
-                    res.z = T(0);
-                    res.w = T(0);
+                if constexpr (HALF) {
+                    if (q == NV4 - 1) {
+                        res.z = T(0);
+                        res.w = T(0);
+                    } else {
+                        res.z = T(double(T(double(acc_hi[q][o].x) + ws * double(cc.z))) / tot);
+                        res.w = T(double(T(double(acc_hi[q][o].y) + ws * double(cc.w))) / tot);
+                    }
                 } else {
                     res.z = T(double(T(double(acc_hi[q][o].x) + ws * double(cc.z))) / tot);
                     res.w = T(double(T(double(acc_hi[q][o].y) + ws * double(cc.w))) / tot);
