@@ -36,6 +36,9 @@
                                  //    chunk (slow; lets compute-sanitizer's racecheck, which does not model remote mbarrier
                                  //    arrivals, verify the data flow itself)
 #endif
+#ifndef NDNLM_NO_PAIRED
+#define NDNLM_NO_PAIRED 0   // 1 (tuning experiment): plain 3-term column sums instead of the pair-sharing variant
+#endif
 #ifndef NDNLM_FOLD_T
 #define NDNLM_FOLD_T double   // type of the second-level weight-sum accumulators
 #endif
@@ -502,7 +505,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 s[e] = sq.x + sq.y;
             }
             T pr[L];
-            if constexpr (FR == 1 && FW > 0) column_box_sum_paired<L>(s, pr);
+            if constexpr (FR == 1 && FW > 0 && !NDNLM_NO_PAIRED) column_box_sum_paired<L>(s, pr);
             else column_box_sum<FR, L>(s, pr);
             P2 px[L / 2];
 #pragma unroll
