@@ -73,6 +73,7 @@ static inline unsigned blocks_for(long long total, int threads) { return unsigne
 
 struct TiledInst {
     int elem;           // bytes per element of the staged cube the kernel computes in: 4 (float) or 8 (double)
+    int minb;           // CTAs per SM the kernel is compiled for (__launch_bounds__ min blocks)
     bool half;          // the last variable group carries at most two variables (V = 5, 6): its upper lanes are skipped
     int nv4, fw, fx, fr, L, nwarps, ch;
     bool neff;
@@ -103,19 +104,19 @@ struct TiledInst {
 
 #define TILED_INSTH(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                \
     {                                                                                                \
-        4, true, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+        4, tiled_min_blocks<float, NV4, FW, L, NW>(), true, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
             launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF, true>,                             \
             "nlm_tiled<nv4=" #NV4 "(half),f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
     },
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
     {                                                                                                \
-        4, false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+        4, tiled_min_blocks<float, NV4, FW, L, NW>(), false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
             launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF>,                                   \
             "nlm_tiled<nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
     },
 #define TILED_INST64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                               \
     {                                                                                                \
-        8, false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<double, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+        8, 1, false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<double, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
             launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF>,                                  \
             "nlm_tiled<double,nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
     },
@@ -193,6 +194,9 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti, int elem) {
     const int ntw = 2 * P.rad[0] + 1;
     bool fits = false;
     size_t smem = 0;
+    // kernels compiled for two CTAs per SM first look for a pass count whose box lets two CTAs share the SM's shared memory
+    size_t cap = ti.minb > 1 ? (kMaxSmem / ti.minb - 1024) : kMaxSmem;
+    for (int attempt = 0; attempt < 2 && !fits; ++attempt, cap = kMaxSmem)
     for (int npass = 1; npass <= ntw && !fits; ++npass) {
         const int per = (ntw + npass - 1) / npass;
         P.npass = (ntw + per - 1) / per;
@@ -206,7 +210,7 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti, int elem) {
             if (P.b[k] > 256) ok = false;
         const size_t plane = ((size_t(P.b[0]) * P.b[1] * P.b[2] + 7) / 8) * 8;
         smem = size_t(ti.nv4) * plane * (4 * size_t(elem)) + ti.exch_bytes + 16 + 16 * size_t(ti.nwarps);
-        fits = ok && smem <= kMaxSmem;
+        fits = ok && smem <= cap;
     }
     if (!fits) return false;
     long long tiles = 1;

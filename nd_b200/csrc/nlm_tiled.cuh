@@ -257,8 +257,16 @@ struct TiledCfg {
 // HALF: the last variable group holds at most two real variables (V = 5 or 6 of 8): its upper two lanes are zero
 // padding, and every load, difference, square and accumulation on them is skipped (64-bit instead of 128-bit
 // shared-memory loads, 3 instead of 4 packed operations per voxel pair, a quarter fewer registers for that group).
+// Small-footprint instantiations (float, one variable group, no W exchange, L <= 4, <= 8 warps) are compiled for two
+// CTAs per SM: 2-D images have few offsets per tile, so the TMA wait and the epilogue of one CTA should overlap the
+// arithmetic of another.
+template <typename T, int NV4, int FW, int L, int NWARPS>
+constexpr int tiled_min_blocks() {
+    return (sizeof(T) == 4 && NV4 == 1 && L <= 4 && NWARPS <= 8) ? 2 : 1;
+}
+
 template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF, bool HALF = false>
-__global__ void __launch_bounds__(NWARPS * 32, 1)
+__global__ void __launch_bounds__(NWARPS * 32, tiled_min_blocks<T, NV4, FW, L, NWARPS>())
 nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                  const typename Elem<T>::V4* __restrict__ padded, typename Elem<T>::V4* __restrict__ out,
                  int* __restrict__ err) {
