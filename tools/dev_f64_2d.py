@@ -1,5 +1,7 @@
+#!/usr/bin/env python
+"""Development timing (GPU): float64 2-D instantiations, forced by index.  Usage: dev_f64_2d.py IDX [IDX ...]"""
 import os, sys
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from nd_b200 import device
 for var in sys.argv[1:]:
