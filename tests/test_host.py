@@ -283,3 +283,54 @@ def test_nlmeans_variables_declines_what_it_cannot_stream():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             nlmeans_variables(a, o, u(2, 2, 1), u(1, 1, 1), 1, 1)
+
+
+def test_apply_streams_per_variable_arrays_and_falls_back(monkeypatch):
+    """Host plumbing of `Filter.apply` for per_variable=False filters (no GPU: the two kernels entry points are
+    replaced by NumPy stand-ins): variables that already have the kernel's layout go to `_filter_variables` one array
+    each, everything else is gathered into the (dims..., variable) block of the reference and goes to `_filter`;
+    dims / coords / attrs / untouched variables come out as the reference's `apply` leaves them (nd/filters.py:105-191)."""
+    from nd_b200.dataset import generate_test_dataset
+    calls = []
+
+    class Doubler(NLMeansFilter):
+        def _filter_variables(self, arrays, axes, outputs):
+            calls.append(("vars", len(arrays), arrays[0].shape, axes))
+            for a, o in zip(arrays, outputs):
+                o[...] = 2 * a
+            return True
+
+        def _filter(self, arr, axes, output):
+            calls.append(("block", arr.shape, axes))
+            output[...] = 3 * arr
+
+    ds = generate_test_dataset(dims={'y': 12, 'x': 9, 'time': 4})
+    ds['mask'] = (('y', 'x'), np.ones((12, 9)))
+    ds.attrs['crs'] = 'EPSG:4326'
+    out = Doubler(dims=('y', 'x', 'time'), r=1).apply(ds)
+    assert calls == [("vars", 4, (12, 9, 4), (0, 1, 2))]
+    for v in ('C11', 'C22', 'C12__re', 'C12__im'):
+        assert np.array_equal(out[v].values, 2 * ds_values(ds, v)) and out[v].dims == ('y', 'x', 'time')
+    assert np.array_equal(out['mask'].values, ds['mask'].values) and out['mask'].values is not ds['mask'].values
+    assert dict(out.attrs) == dict(ds.attrs) and all(np.array_equal(out.coords[c], ds.coords[c]) for c in ds.coords)
+    assert list(ds.data_vars) == ['C11', 'C12__im', 'C12__re', 'C22', 'mask']       # the input is left as it was
+
+    # filter dims in another order than the variables' dims: the reference's gather / transpose path
+    calls.clear()
+    out2 = Doubler(dims=('x', 'y'), r=1).apply(ds)
+    assert calls and calls[0][0] == "block" and calls[0][1] == (9, 12, 4, 4)
+    assert np.array_equal(out2['C11'].values, 3 * ds['C11'].values) and out2['C11'].dims == ('y', 'x', 'time')
+
+    # a filter that declines (returns False) falls back to the block path too
+    calls.clear()
+    monkeypatch.setattr(Doubler, "_filter_variables", lambda self, a, ax, o: False)
+    out3 = Doubler(dims=('y', 'x', 'time'), r=1).apply(ds)
+    assert [c[0] for c in calls] == ["block"] and np.array_equal(out3['C22'].values, 3 * ds['C22'].values)
+
+
+def ds_values(ds, name):
+    """Values of a (possibly complex-split) variable of the stand-in Dataset after `apply` reassembled the input."""
+    if name in ds.data_vars:
+        return ds[name].values
+    stem, part = name.rsplit('__', 1)
+    return ds[stem].values.real if part == 're' else ds[stem].values.imag
