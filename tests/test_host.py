@@ -317,6 +317,7 @@ def test_apply_streams_per_variable_arrays_and_falls_back(monkeypatch):
 
     # filter dims in another order than the variables' dims: the reference's gather / transpose path
     calls.clear()
+    del ds['mask']                       # (a 2-D variable beside 3-D ones would be filtered too with dims=('x','y'))
     out2 = Doubler(dims=('x', 'y'), r=1).apply(ds)
     assert calls and calls[0][0] == "block" and calls[0][1] == (9, 12, 4, 4)
     assert np.array_equal(out2['C11'].values, 3 * ds['C11'].values) and out2['C11'].dims == ('y', 'x', 'time')
