@@ -257,12 +257,12 @@ struct TiledCfg {
 // HALF: the last variable group holds at most two real variables (V = 5 or 6 of 8): its upper two lanes are zero
 // padding, and every load, difference, square and accumulation on them is skipped (64-bit instead of 128-bit
 // shared-memory loads, 3 instead of 4 packed operations per voxel pair, a quarter fewer registers for that group).
-// Small-footprint instantiations (float, one variable group, no W exchange, L <= 4, <= 8 warps) are compiled for two
-// CTAs per SM: 2-D images have few offsets per tile, so the TMA wait and the epilogue of one CTA should overlap the
-// arithmetic of another.
+// Small-footprint instantiations (float, one variable group, L <= 4) are compiled for several CTAs per SM -- 4 for the
+// 4-warp kernels of 2-D images / batch axes, 2 for the 8-warp fallbacks: 2-D images have few offsets per tile, so the
+// TMA wait and the epilogue of one CTA should overlap the arithmetic of the others.
 template <typename T, int NV4, int FW, int L, int NWARPS>
 constexpr int tiled_min_blocks() {
-    return (sizeof(T) == 4 && NV4 == 1 && L <= 4 && NWARPS <= 8) ? 2 : 1;
+    return (sizeof(T) == 4 && NV4 == 1 && L <= 4 && NWARPS <= 4) ? 4 : (sizeof(T) == 4 && NV4 == 1 && L <= 4 && NWARPS <= 8) ? 2 : 1;
 }
 
 template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF, bool HALF = false>
