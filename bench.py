@@ -409,8 +409,13 @@ def run_ours(args):
 
     # ---- parity samples (rank 0 checks its own rows, including the seam with rank 1) ----
     seams = []
-    if streamed and ny > wl["slab_rows"]:
-        seams.append(("slab_seam", wl["slab_rows"]))
+    slab_rows = 0
+    if streamed:
+        # the slab height the streaming layer really uses: the requested one rounded to whole kernel tiles
+        slab_rows = nstream.device_slab_rows(ny, (nx, nt, V), wl["r"], fvec(wl), wl["sigma"], wl["h"], -1,
+                                             semantics=sem, slab_rows=wl["slab_rows"])
+    if streamed and ny > slab_rows:
+        seams.append(("slab_seam", slab_rows))
     if world > 1 and ny == shard_rows:
         seams.append(("rank_seam", ny - 1))
     samples = parity_samples(wl, ny, global_rows, world, seams) if rank == 0 else []
@@ -677,7 +682,7 @@ def run_ours(args):
                     if alg_bytes / 2 > 126e6 else "input %.1f MB fits in L2 (tiny reference-sized workload)" % (alg_bytes / 2e6),
               "plan": plan_info}
     if streamed:
-        config["streaming"] = {"slab_rows": wl["slab_rows"], "slabs_per_step": kernel_launches_per_step,
+        config["streaming"] = {"slab_rows": slab_rows, "slabs_per_step": kernel_launches_per_step,
                                "source": "each slab is synthesised on the device by global index inside the timed region",
                                "checksum": float(state["checksum"].item()) if state["checksum"] is not None else None}
         config["sweep"] = {"rows_per_gpu_processed": ny, "rows_per_gpu_total": shard_rows,

@@ -75,6 +75,7 @@ struct TiledInst {
     int elem;           // bytes per element of the staged cube the kernel computes in: 4 (float) or 8 (double)
     int minb;           // CTAs per SM the kernel is compiled for (__launch_bounds__ min blocks)
     bool half;          // the last variable group carries at most two variables (V = 5, 6): its upper lanes are skipped
+    bool dh;            // double-duty halo warps (nlm_tiled.cuh, TiledCfg): nwarps warps cover nwarps + fw rows
     int nv4, fw, fx, fr, L, nwarps, ch;
     bool neff;
     size_t exch_bytes;
@@ -92,31 +93,53 @@ struct TiledInst {
 #define TILED_INSTH(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                       \
     extern template cudaError_t launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF, true>(                  \
         const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
+#define TILED_INSTD(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                       \
+    extern template cudaError_t launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF, false, true>(           \
+        const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
+#define TILED_INSTD64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                     \
+    extern template cudaError_t launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF, false, true>(          \
+        const CUtensorMap&, const ndnlm::DevParams&, const void*, void*, int*, int, size_t, cudaStream_t);
 #include "instances_g0.inc"
 #include "instances_g1.inc"
 #include "instances_g2.inc"
 #include "instances_g3.inc"
 #include "instances_g4.inc"
 #include "instances_g5.inc"
+#include "instances_g6.inc"
 #undef TILED_INST
 #undef TILED_INST64
 #undef TILED_INSTH
+#undef TILED_INSTD
+#undef TILED_INSTD64
 
+#define TILED_INSTD64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                              \
+    {                                                                                                \
+        8, 1, false, true, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<double, NV4, FW, FX, FR, L, NW, CH, NEFF, true>::EXCH_BYTES, \
+            launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF, false, true>,                     \
+            "nlm_tiled<double,nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW "(dh),ch=" #CH ",neff=" #NEFF ">" \
+    },
+
+#define TILED_INSTD(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                \
+    {                                                                                                \
+        4, 1, false, true, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF, true>::EXCH_BYTES, \
+            launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF, false, true>,                      \
+            "nlm_tiled<nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW "(dh),ch=" #CH ",neff=" #NEFF ">" \
+    },
 #define TILED_INSTH(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                \
     {                                                                                                \
-        4, tiled_min_blocks<float, NV4, FW, L, NW>(), true, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+        4, tiled_min_blocks<float, NV4, FW, L, NW>(), true, false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
             launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF, true>,                             \
             "nlm_tiled<nv4=" #NV4 "(half),f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
     },
 #define TILED_INST(NV4, FW, FX, FR, L, NW, CH, NEFF)                                                 \
     {                                                                                                \
-        4, tiled_min_blocks<float, NV4, FW, L, NW>(), false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+        4, tiled_min_blocks<float, NV4, FW, L, NW>(), false, false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<float, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
             launch_tiled<float, NV4, FW, FX, FR, L, NW, CH, NEFF>,                                   \
             "nlm_tiled<nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
     },
 #define TILED_INST64(NV4, FW, FX, FR, L, NW, CH, NEFF)                                               \
     {                                                                                                \
-        8, 1, false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<double, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
+        8, 1, false, false, NV4, FW, FX, FR, L, NW, CH, NEFF, TiledCfg<double, NV4, FW, FX, FR, L, NW, CH, NEFF>::EXCH_BYTES, \
             launch_tiled<double, NV4, FW, FX, FR, L, NW, CH, NEFF>,                                  \
             "nlm_tiled<double,nv4=" #NV4 ",f=(" #FW "," #FR "," #FX "),L=" #L ",warps=" #NW ",ch=" #CH ",neff=" #NEFF ">" \
     },
@@ -129,10 +152,13 @@ static const TiledInst g_tiled[] = {
 #include "instances_g3.inc"
 #include "instances_g4.inc"
 #include "instances_g5.inc"
+#include "instances_g6.inc"
 };
 #undef TILED_INST
 #undef TILED_INST64
 #undef TILED_INSTH
+#undef TILED_INSTD
+#undef TILED_INSTD64
 static const int g_ntiled = int(sizeof(g_tiled) / sizeof(g_tiled[0]));
 
 // ------------------------------------------------------------------------------------------
@@ -159,6 +185,9 @@ struct ndnlm_plan {
 };
 
 static const size_t kMaxSmem = 232448;   // 227 KB per CTA on sm_100a
+#ifndef NDNLM_DH_MIN_FW
+#define NDNLM_DH_MIN_FW 2                // double-duty-halo-warp instantiations are preferred from this W patch radius on
+#endif
 
 static int largest_divisor_leq(int n, int cap) {
     int best = 1;
@@ -177,7 +206,7 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti, int elem) {
     const int txw = 32 - 2 * ti.fx;
     int gw, gr, gx;
     if (ti.fw > 0) {
-        gw = ti.nwarps;
+        gw = ti.dh ? ti.nwarps + ti.fw : ti.nwarps;     // W rows of the CTA tile (patch-halo rows included)
         gr = gx = 1;
     } else {
         gw = largest_divisor_leq(ti.nwarps, P.n[0] < 1 ? 1 : P.n[0]);
@@ -209,7 +238,7 @@ static bool configure_tiled(ndnlm_plan* pl, const TiledInst& ti, int elem) {
         for (int k = 0; k < 3; ++k)
             if (P.b[k] > 256) ok = false;
         const size_t plane = ((size_t(P.b[0]) * P.b[1] * P.b[2] + 7) / 8) * 8;
-        smem = size_t(ti.nv4) * plane * (4 * size_t(elem)) + ti.exch_bytes + 16 + 16 * size_t(ti.nwarps);
+        smem = size_t(ti.nv4) * plane * (4 * size_t(elem)) + ti.exch_bytes + 16 + 16 * size_t(ti.fw > 0 ? gw : ti.nwarps);
         fits = ok && smem <= cap;
     }
     if (!fits) return false;
@@ -343,12 +372,21 @@ extern "C" int ndnlm_plan_create_roles(ndnlm_plan_t** out_plan, const int64_t sh
     if (kernel != NDNLM_KERNEL_GENERIC && tiled_ok) {
         const char* venv = getenv("NDNLM_TILED_VARIANT");   // tuning aid: force one instantiation
         const int forced = venv ? atoi(venv) : -1;
-        for (int i = 0; i < g_ntiled; ++i) {
-            if (forced >= 0 && i != forced) continue;
-            if (configure_tiled(pl, g_tiled[i], elem)) {
-                pl->kernel = NDNLM_KERNEL_TILED;
-                pl->inst = i;
-                break;
+        // Two rounds over the table: the double-duty-halo-warp instantiations (instances_g6.inc) first where they are
+        // enabled (by default for patch radius f_W >= NDNLM_DH_MIN_FW; NDNLM_DH=0 / 1 disables / enables all of them),
+        // then everything else in file order.
+        const char* denv = getenv("NDNLM_DH");
+        for (int round = 0; round < 2 && pl->inst < 0; ++round) {
+            for (int i = 0; i < g_ntiled; ++i) {
+                if (forced >= 0 && i != forced) continue;
+                // measured (profiles/r2_dh_*): +15 % with four halo rows (f_W = 2), -1 % with two (f_W = 1)
+                const bool use_dh = denv ? atoi(denv) != 0 : (g_tiled[i].fw >= NDNLM_DH_MIN_FW);
+                if (forced < 0 && (g_tiled[i].dh != (round == 0) || (g_tiled[i].dh && !use_dh))) continue;
+                if (configure_tiled(pl, g_tiled[i], elem)) {
+                    pl->kernel = NDNLM_KERNEL_TILED;
+                    pl->inst = i;
+                    break;
+                }
             }
         }
     }

@@ -245,13 +245,19 @@ __device__ __forceinline__ P2 lane_box_sum2(const P2 v) {
     }
 }
 
-template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF>
+// DH ("double-duty halo warps", FW > 0 only): the 2 FW patch-halo rows of a CTA tile only run phase A (squared
+// differences, R / X sums, publish) -- about half the work of a row that also weighs and accumulates.  With one warp per
+// row they leave their warp scheduler under-used and occupy 2 FW of the NWARPS register-file slots.  With DH each of FW
+// halo WARPS serves TWO halo rows (one above, one below the valid rows; it keeps no accumulators, so the second centre
+// column fits its registers): NWARPS warps then cover NWARPS + FW rows, NWARPS - FW of them valid.
+template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF, bool DH = false>
 struct TiledCfg {
     static constexpr int E = L + 2 * FR;      // column elements including the patch halo
     static constexpr int WN = E + CH - 1;     // neighbour window elements per chunk of CH R-offsets
     static constexpr int TXW = 32 - 2 * FX;   // valid lanes per warp
     static constexpr int THREADS = NWARPS * 32;
-    static constexpr size_t EXCH_BYTES = FW > 0 ? size_t(CH) * NWARPS * (L / 2) * 32 * sizeof(typename Elem<T>::P2) : 0;
+    static constexpr int NROWS = DH ? NWARPS + FW : NWARPS;   // W rows of the CTA tile, patch-halo rows included
+    static constexpr size_t EXCH_BYTES = FW > 0 ? size_t(CH) * NROWS * (L / 2) * 32 * sizeof(typename Elem<T>::P2) : 0;
 };
 
 // HALF: the last variable group holds at most two real variables (V = 5 or 6 of 8): its upper two lanes are zero
@@ -265,17 +271,19 @@ constexpr int tiled_min_blocks() {
     return (sizeof(T) == 4 && NV4 == 1 && L <= 4 && NWARPS <= 4) ? 4 : (sizeof(T) == 4 && NV4 == 1 && L <= 4 && NWARPS <= 8) ? 2 : 1;
 }
 
-template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF, bool HALF = false>
+template <typename T, int NV4, int FW, int FX, int FR, int L, int NWARPS, int CH, bool NEFF, bool HALF = false, bool DH = false>
 __global__ void __launch_bounds__(NWARPS * 32, tiled_min_blocks<T, NV4, FW, L, NWARPS>())
 nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                  const typename Elem<T>::V4* __restrict__ padded, typename Elem<T>::V4* __restrict__ out,
                  int* __restrict__ err) {
-    using Cfg = TiledCfg<T, NV4, FW, FX, FR, L, NWARPS, CH, NEFF>;
+    using Cfg = TiledCfg<T, NV4, FW, FX, FR, L, NWARPS, CH, NEFF, DH>;
     using V4 = typename Elem<T>::V4;
     using P2 = typename Elem<T>::P2;
     constexpr bool F64 = sizeof(T) == 8;
     static_assert(L % 2 == 0, "L must be even (outputs are exchanged in pairs)");
+    static_assert(!DH || (FW > 0 && NWARPS >= 3 * FW + 1), "double-duty halo warps need a W patch axis");
     constexpr int E = Cfg::E, TXW = Cfg::TXW;
+    constexpr int NROWS = Cfg::NROWS;                      // W rows of the tile (== NWARPS unless DH)
 
     // Shared memory: the padded box as [q][BW][BX][BRP] float4 -- R is the FASTEST axis and its
     // pitch BRP is odd, so a thread's column / neighbour window is a run of consecutive float4
@@ -292,7 +300,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     //             source row, so a reader waits ONCE)
     //   empty[w]  every warp that reads warp w's sums has finished with them              (one arrival per reader)
     uint64_t* mbar_full = mbar + 1;
-    uint64_t* mbar_empty = mbar + 1 + NWARPS;
+    uint64_t* mbar_empty = mbar + 1 + NROWS;
 
     int bid = blockIdx.x;
     const int tileX = bid % P.tiles[2];
@@ -305,13 +313,13 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         if constexpr (FW > 0) {
-            for (int w = 0; w < NWARPS; ++w) {
-                int readers = 0;   // valid warps within FW rows of w, other than w itself
+            for (int w = 0; w < NROWS; ++w) {
+                int readers = 0;   // valid rows within FW rows of w, other than w itself
                 for (int d = -FW; d <= FW; ++d)
-                    if (d != 0 && w + d >= FW && w + d < NWARPS - FW) ++readers;
+                    if (d != 0 && w + d >= FW && w + d < NROWS - FW) ++readers;
                 int sources = 0;   // rows within FW of w, other than w itself (the rows w reads)
                 for (int d = -FW; d <= FW; ++d)
-                    if (d != 0 && w + d >= 0 && w + d < NWARPS) ++sources;
+                    if (d != 0 && w + d >= 0 && w + d < NROWS) ++sources;
                 mbar_init(mbar_full + w, sources);                         // "every row I read is published"
                 mbar_init(mbar_empty + w, readers > 0 ? readers : 1);      // "every reader of my row is done"
             }
@@ -355,10 +363,13 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     const int gxw = (FW > 0) ? 1 : P.g[2], grw = (FW > 0) ? 1 : P.g[1];
     const int wx = wid % gxw;
     const int wr = (wid / gxw) % grw;
-    const int ww = wid / (gxw * grw);
+    // W row inside the CTA tile.  DH: warps 0 .. NWARPS-FW-1 own the valid rows FW .. NROWS-FW-1, halo warp k (the last
+    // FW warps) owns the halo rows k (above) and NROWS-FW+k (below)
+    const int ww = DH ? (wid >= NWARPS - FW ? wid - (NWARPS - FW) : wid + FW) : wid / (gxw * grw);
     const int lx = wx * TXW + lane + P.rad[2];
     const int lr0 = wr * L + P.rad[1];
-    const bool wvalid = (FW == 0) || (ww >= FW && ww < NWARPS - FW);
+    const bool wvalid = (FW == 0) || (ww >= FW && ww < NROWS - FW);
+    const int xw = DH ? ww : wid;                          // my row's index among the exchange slots / mbarriers
 
     // centre column: read once, straight from the padded cube (R is the fastest axis there too)
     V4 c[NV4][E];
@@ -416,13 +427,13 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
     const T c2s = F64 ? T(P.two_sigma2 * P.inv_h2) : T(P.c2);
     const P2 c1 = mk2(c1s, c1s);
     const P2 nc2 = mk2(-c2s, -c2s);
-    P2* const ex_own = exch + (wid * (L / 2)) * 32 + lane;     // + (j*NWARPS*(L/2) + o2)*32
-    constexpr int EX_J = NWARPS * (L / 2) * 32;                     // float2 stride between R-offsets j
+    P2* const ex_own = exch + (xw * (L / 2)) * 32 + lane;     // + (j*NWARPS*(L/2) + o2)*32
+    constexpr int EX_J = NROWS * (L / 2) * 32;                      // float2 stride between R-offsets j
     constexpr int EX_ROW = (L / 2) * 32;                            // float2 stride between W rows (FW>0: 1 warp/row)
-    [[maybe_unused]] V4* const ex_own4 = reinterpret_cast<V4*>(exch) + wid * 32 + lane;   // L == 4 layout
-    [[maybe_unused]] constexpr int EX_J4 = NWARPS * 32;             // float4 stride between R-offsets j
+    [[maybe_unused]] V4* const ex_own4 = reinterpret_cast<V4*>(exch) + xw * 32 + lane;   // L == 4 layout
+    [[maybe_unused]] constexpr int EX_J4 = NROWS * 32;              // float4 stride between R-offsets j
     uint32_t xpar = 0;                                              // parity of the current exchange round
-    static_assert(FW == 0 || NWARPS >= 2 * FW + 2, "every row needs at least one reader");
+    static_assert(FW == 0 || NROWS >= 2 * FW + 2, "every row needs at least one reader");
 
     // One chunk of NJ consecutive R-offsets [ch0, ch0+NJ).  NJ is a compile-time constant so the body is
     // straight-line code the scheduler can interleave freely.  CENTRE: the chunk contains the centre
@@ -431,7 +442,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         constexpr int NJ = decltype(nj_tag)::value;
         constexpr bool CENTRE = decltype(centre_tag)::value;
         constexpr int WNJ = E + NJ - 1;
-        if constexpr (CENTRE && FW > 0 && !NDNLM_DEBUG_CTA_SYNC) mbar_wait(mbar_empty + wid, xpar ^ 1);
+        if constexpr (CENTRE && FW > 0 && !NDNLM_DEBUG_CTA_SYNC) mbar_wait(mbar_empty + xw, xpar ^ 1);
         [[maybe_unused]] P2 own[NDNLM_KEEP_OWN != 0 ? NJ : 1][L / 2];
 
         V4 n[NV4][WNJ];
@@ -524,7 +535,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 // before the first store of this chunk: my readers must be done with the previous round
                 // (on a fresh barrier the wait for the "previous" parity returns at once)
                 if constexpr (!CENTRE && !NDNLM_DEBUG_CTA_SYNC) {
-                    if (j == 0) mbar_wait(mbar_empty + wid, xpar ^ 1);
+                    if (j == 0) mbar_wait(mbar_empty + xw, xpar ^ 1);
                 }
                 if constexpr (L == 4) {
                     // one 16-B store / load per row and offset: [j][row][lane] float4
@@ -547,10 +558,10 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
             // release: my sums are published -- tell every valid row that reads them (lanes 0..2FW-1, one each)
             if (!NDNLM_DEBUG_CTA_SYNC && lane < 2 * FW) {
                 const int d = (lane < FW) ? lane - FW : lane - FW + 1;
-                if (wid + d >= FW && wid + d < NWARPS - FW) mbar_arrive(mbar_full + wid + d);
+                if (xw + d >= FW && xw + d < NROWS - FW) mbar_arrive(mbar_full + xw + d);
             }
             if (wvalid) {
-                if constexpr (!NDNLM_DEBUG_CTA_SYNC) mbar_wait(mbar_full + wid, xpar);   // acquire: all rows I read are published
+                if constexpr (!NDNLM_DEBUG_CTA_SYNC) mbar_wait(mbar_full + xw, xpar);   // acquire: all rows I read are published
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     if constexpr (CENTRE) {
@@ -589,7 +600,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                 __syncwarp();
                 if (!NDNLM_DEBUG_CTA_SYNC && lane < 2 * FW) {         // done reading the neighbour rows
                     const int d = (lane < FW) ? lane - FW : lane - FW + 1;
-                    mbar_arrive(mbar_empty + wid + d);
+                    mbar_arrive(mbar_empty + xw + d);
                 }
             }
             if constexpr (NDNLM_DEBUG_CTA_SYNC) __syncthreads();
@@ -614,6 +625,110 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
         }
     };
     const int nR = 2 * rR + 1;
+    if constexpr (DH) {
+        if (ww < FW) {
+            // ---- a double-duty halo warp: phase A only, for its two rows ww (above the valid rows) and ww2 (below) ----
+            // It keeps no accumulators (their registers hold the second centre column), runs the same sweep over passes
+            // and offsets as the other warps with the same CTA barriers (one per pass change, those of load_pass), and
+            // leaves before the epilogue.  The arithmetic is phase A of `chunk` above, expression by expression: the
+            // sums a halo row publishes must not depend on which kind of warp computed them.
+            const int ww2 = NROWS - FW + ww;
+            V4 c2[NV4][E];
+            {
+                const int gw = w0 + ww2 + P.rad[0], gx = x0 + lx;
+                const bool inb = gw < P.pd[0] && gx < P.pd[2];
+#pragma unroll
+                for (int q = 0; q < NV4; ++q)
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const int gr = r0 + lr0 + e;
+                        c2[q][e] = (inb && gr < P.pd[1])
+                                       ? padded[((size_t(q) * P.pd[0] + gw) * P.pd[2] + gx) * P.pd[1] + gr]
+                                       : mk4(T(0), T(0), T(0), T(0));
+                    }
+            }
+            static_assert(!DH || !HALF, "no half-group variant of the double-duty halo warps");
+            auto halo_chunk = [&](auto nj_tag, auto centre_tag, const V4 (&cc)[NV4][E], const int hrow, const uint32_t par,
+                                  const V4* nb, const int ch0) {
+                constexpr int NJ = decltype(nj_tag)::value;
+                constexpr bool CENTRE = decltype(centre_tag)::value;
+                constexpr int WNJ = E + NJ - 1;
+                V4 n[NV4][WNJ];
+#pragma unroll
+                for (int k = 0; k < WNJ; ++k)
+#pragma unroll
+                    for (int q = 0; q < NV4; ++q) n[q][k] = nb[size_t(q) * plane + k];
+                // my readers must be done with the previous round before its slots are overwritten
+                if constexpr (!NDNLM_DEBUG_CTA_SYNC) mbar_wait(mbar_empty + hrow, par ^ 1);
+                P2* const ex = exch + (hrow * (L / 2)) * 32 + lane;
+                [[maybe_unused]] V4* const ex4 = reinterpret_cast<V4*>(exch) + hrow * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    if constexpr (CENTRE) {
+                        if (ch0 + j == 0) continue;
+                    }
+                    T s[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        P2 sq;
+#pragma unroll
+                        for (int q = 0; q < NV4; ++q) {
+                            const P2 d0 = padd(lo2(cc[q][e]), pneg(lo2(n[q][e + j])));
+                            const P2 d1 = padd(hi2(cc[q][e]), pneg(hi2(n[q][e + j])));
+                            sq = (q == 0) ? pmul(d0, d0) : pfma(d0, d0, sq);
+                            sq = pfma(d1, d1, sq);
+                        }
+                        s[e] = sq.x + sq.y;
+                    }
+                    T pr[L];
+                    if constexpr (FR == 1 && !NDNLM_NO_PAIRED) column_box_sum_paired<L>(s, pr);
+                    else column_box_sum<FR, L>(s, pr);
+                    P2 px[L / 2];
+#pragma unroll
+                    for (int o2 = 0; o2 < L / 2; ++o2) px[o2] = lane_box_sum2<FX>(mk2(pr[2 * o2], pr[2 * o2 + 1]));
+                    if constexpr (L == 4) {
+                        ex4[j * EX_J4] = mk4(px[0].x, px[0].y, px[1].x, px[1].y);
+                    } else {
+#pragma unroll
+                        for (int o2 = 0; o2 < L / 2; ++o2) ex[j * EX_J + o2 * 32] = px[o2];
+                    }
+                }
+                __syncwarp();
+                if (!NDNLM_DEBUG_CTA_SYNC && lane < 2 * FW) {      // published: tell every valid row that reads this one
+                    const int d = (lane < FW) ? lane - FW : lane - FW + 1;
+                    if (hrow + d >= FW && hrow + d < NROWS - FW) mbar_arrive(mbar_full + hrow + d);
+                }
+            };
+            uint32_t hpar = 0;
+            const int drow = (ww2 - ww) * BX * BRP;
+            for (int pass = 0; pass < P.npass; ++pass) {
+                const int twa = -rW + pass * P.ntw_pass;
+                const int twb = min(rW, twa + P.ntw_pass - 1);
+                if (pass > 0) __syncthreads();
+                load_pass(pass);
+                for (int tw = twa; tw <= twb; ++tw) {
+                    for (int tx = -rX; tx <= rX; ++tx) {
+                        const V4* nb0 = tile + ((ww + tw - twa) * BX + lx + tx) * BRP + lr0;
+                        const bool centre_step = (tw == 0) & (tx == 0);
+                        for (int ch0 = -rR; ch0 <= rR; ch0 += CH) {
+                            const int nj = min(CH, rR - ch0 + 1);                        // uniform
+                            const bool centre = centre_step && ch0 <= 0 && ch0 + nj > 0;
+                            dispatch_chunk<CH>(nj, centre, [&](auto nj_tag, auto centre_tag) {
+                                halo_chunk(nj_tag, centre_tag, c, ww, hpar, nb0 + ch0, ch0);
+                                halo_chunk(nj_tag, centre_tag, c2, ww2, hpar, nb0 + drow + ch0, ch0);
+                            });
+                            if constexpr (NDNLM_DEBUG_CTA_SYNC) {      // the two CTA barriers of `chunk` in that mode
+                                __syncthreads();
+                                __syncthreads();
+                            }
+                            hpar ^= 1;
+                        }
+                    }
+                }
+            }
+            return;
+        }
+    }
     for (int pass = 0; pass < P.npass; ++pass) {
         const int twa = -rW + pass * P.ntw_pass;
         const int twb = min(rW, twa + P.ntw_pass - 1);

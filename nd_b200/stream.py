@@ -255,6 +255,26 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
     return sp.nshards
 
 
+def device_slab_rows(n0, inner_shape, r3, f3, sigma, h, n_eff=-1, semantics=None, kernel='auto', slab_rows=None,
+                     dtype=np.float32):
+    """Rows per slab `apply_device_streamed` uses for these arguments: the requested (or ~4 GiB) height rounded down
+    to a whole number of kernel tiles along axis 0, so that no tile row of a slab is partly empty."""
+    n0 = int(n0)
+    inner_shape = tuple(int(x) for x in inner_shape)
+    halo = int(r3[0]) + int(f3[0])
+    if slab_rows is None:
+        row_bytes = np.dtype(dtype).itemsize * int(np.prod(inner_shape))
+        slab_rows = max(4 * halo + 16, min(n0, (4 << 30) // max(row_bytes, 1)))
+    slab_rows = min(int(slab_rows), n0)
+    probe = dev.Plan((max(slab_rows, halo + 1),) + inner_shape, r3, f3, sigma, h, n_eff, semantics=semantics,
+                     dtype=dtype, kernel=kernel)
+    if probe.is_tiled and slab_rows < n0:
+        tile0 = int(probe.info.tile[list(probe.info.role_axis).index(0)])
+        if tile0 > 0:
+            slab_rows = max(tile0, slab_rows // tile0 * tile0)
+    return slab_rows
+
+
 def apply_device_streamed(source, sink, n0, inner_shape, r3, f3, sigma, h, n_eff=-1, semantics=None, kernel='auto',
                           slab_rows=None, lo_rows=None, hi_rows=None, dtype=np.float32, on_kernel=None):
     """Filter a cube of `n0` rows that is PRODUCED and CONSUMED slab by slab on the device -- cubes (or y-shards
@@ -275,20 +295,11 @@ def apply_device_streamed(source, sink, n0, inner_shape, r3, f3, sigma, h, n_eff
     halo = int(r3[0]) + int(f3[0])
     device = torch.device('cuda', torch.cuda.current_device())
     tdtype = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
-    itemsize = np.dtype(dtype).itemsize
     for nb in (lo_rows, hi_rows):
         if nb is not None and tuple(nb.shape) != (halo,) + inner_shape:
             raise ValueError('neighbour rows must have shape %s' % ((halo,) + inner_shape,))
-    if slab_rows is None:
-        row_bytes = itemsize * int(np.prod(inner_shape))
-        slab_rows = max(4 * halo + 16, min(n0, (4 << 30) // max(row_bytes, 1)))
-    slab_rows = min(int(slab_rows), n0)
-    probe = dev.Plan((max(slab_rows, halo + 1),) + inner_shape, r3, f3, sigma, h, n_eff, semantics=semantics,
-                     dtype=dtype, kernel=kernel)
-    if probe.is_tiled and slab_rows < n0:
-        tile0 = int(probe.info.tile[list(probe.info.role_axis).index(0)])
-        if tile0 > 0:
-            slab_rows = max(tile0, slab_rows // tile0 * tile0)
+    slab_rows = device_slab_rows(n0, inner_shape, r3, f3, sigma, h, n_eff, semantics=semantics, kernel=kernel,
+                                 slab_rows=slab_rows, dtype=dtype)
     sp = ShardPlan.from_rows(n0, slab_rows, halo)
     max_int = max(hi - lo for lo, hi in sp.ranges)
     d_in = torch.empty((max_int + 2 * halo,) + inner_shape, dtype=tdtype, device=device)

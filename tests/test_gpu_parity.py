@@ -281,6 +281,40 @@ def test_deterministic(dev):
     assert np.array_equal(o1, o2)
 
 
+@pytest.mark.parametrize("dtype,r,f,shape", [
+    (np.float32, (3, 3, 2), (1, 1, 1), (37, 70, 11, 4)),       # f = 1: 15 valid rows per CTA instead of 14
+    (np.float32, (4, 3, 2), (2, 2, 2), (33, 40, 10, 3)),       # f = 2: 10 instead of 8 (the default there)
+    (np.float32, (3, 3, 1), (2, 2, 2), (23, 36, 9, 4)),
+    (np.float64, (2, 3, 1), (1, 1, 1), (19, 40, 9, 2)),        # float64: 7 instead of 6
+    (np.float64, (2, 2, 1), (2, 2, 2), (17, 36, 9, 4)),        # float64, f = 2: 6 instead of 4
+])
+def test_double_duty_halo_warps_equal_plain_instantiations_bitwise(dev, monkeypatch, dtype, r, f, shape):
+    """instances_g6.inc: the halo rows of a CTA tile are served two per warp (no accumulators in those warps).  The
+    arithmetic per voxel is that of the plain instantiations, so the results must agree bit for bit -- and with the
+    oracle.  NDNLM_DH is read at plan creation."""
+    a = sar_like(shape, seed=23, dtype=dtype)
+    monkeypatch.setenv("NDNLM_DH", "0")
+    plain, p0 = run_plan(dev, a, r, f, 0.3, 0.6)
+    monkeypatch.setenv("NDNLM_DH", "1")
+    dh, p1 = run_plan(dev, a, r, f, 0.3, 0.6)
+    assert "(dh)" in p1.kernel_name and "(dh)" not in p0.kernel_name, (p0.kernel_name, p1.kernel_name)
+    assert p1.info.tile[0] > p0.info.tile[0]
+    assert np.array_equal(plain, dh), (p1.kernel_name, float(np.abs(plain - dh).max()))
+    from oracle import c_port
+    assert scaled_err(dh, c_port.nlmeans(a, r, f, 0.3, 0.6)) < (TOL64 if dtype == np.float64 else TOL32)
+
+
+def test_double_duty_halo_warps_n_eff_and_default_choice(dev, monkeypatch):
+    from oracle import c_port
+    a = sar_like((31, 40, 10, 4), seed=29, dtype=np.float32)
+    monkeypatch.delenv("NDNLM_DH", raising=False)
+    out, plan = run_plan(dev, a, (3, 3, 1), (2, 2, 2), 0.4, 0.8, n_eff=30)
+    assert "(dh)" in plan.kernel_name and "neff=true" in plan.kernel_name        # the default for f = 2
+    assert scaled_err(out, c_port.nlmeans(a, (3, 3, 1), (2, 2, 2), 0.4, 0.8, 30)) < TOL32
+    _, p1 = run_plan(dev, a, (3, 3, 1), (1, 1, 1), 0.4, 0.8)
+    assert "(dh)" not in p1.kernel_name                                          # f = 1 keeps one warp per row
+
+
 @pytest.mark.parametrize("nshards", [2, 3])
 def test_sharded_equals_unsharded_bitwise(dev, nshards):
     """The halo layer on ONE GPU (devices=[0,0,..]): y-shards + neighbour halo rows == unsharded, bit for bit

@@ -99,6 +99,26 @@ def test_plan_kernel_selection():
         del os.environ["ND_NLM_FLOAT64_COMPUTE"]
 
 
+def test_double_duty_halo_warp_instantiations_are_chosen_for_f2(monkeypatch):
+    """instances_g6.inc (ndnlm.cu): with four patch-halo rows per CTA tile (f_W = 2) the halo rows are served two per
+    warp -- 10 valid rows of 12 warps instead of 8 -- by default; with two (f_W = 1) only on request."""
+    monkeypatch.delenv("NDNLM_DH", raising=False)
+    cfg4 = device.Plan((256, 16384, 64, 4), (7, 7, 2), (2, 2, 2), 0.25, 0.5)
+    assert "(dh)" in cfg4.kernel_name and list(cfg4.info.tile)[0] == 10 and cfg4.info.smem_bytes <= 232448
+    cfg3 = device.Plan((4096, 4096, 32, 4), (5, 5, 2), (1, 1, 1), 0.25, 0.5)
+    assert "(dh)" not in cfg3.kernel_name and list(cfg3.info.tile)[0] == 14
+    monkeypatch.setenv("NDNLM_DH", "0")
+    plain = device.Plan((256, 16384, 64, 4), (7, 7, 2), (2, 2, 2), 0.25, 0.5)
+    assert "(dh)" not in plain.kernel_name and list(plain.info.tile)[0] == 8
+    assert plain.roles == cfg4.roles and plain.padded_bytes == cfg4.padded_bytes     # same staged layout
+    monkeypatch.setenv("NDNLM_DH", "1")
+    p = device.Plan((4096, 4096, 32, 4), (5, 5, 2), (1, 1, 1), 0.25, 0.5)
+    assert "(dh)" in p.kernel_name and list(p.info.tile)[0] == 15 and p.info.smem_bytes <= 232448
+    # configurations without such an instantiation are unaffected (2-D: no W patch axis; V = 6)
+    assert "(dh)" not in device.Plan((1, 206, 500, 4), (0, 3, 3), (0, 1, 1), 1, 1).kernel_name
+    assert "(dh)" not in device.Plan((64, 256, 128, 6), (10, 10, 3), (2, 2, 2), 1, 1).kernel_name
+
+
 def test_plan_errors_map_to_reference_exceptions():
     with pytest.raises(TypeError):                                   # fused `floating` dispatch failure
         device.Plan((4, 5, 6, 2), (1, 1, 1), (0, 0, 0), 1, 1, dtype=np.int32)
