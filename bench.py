@@ -441,11 +441,11 @@ def run_ours(args):
             if timed:
                 e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 e[0].record()
-            shard.run()
+            shard.run(out)          # C-ordered (y, x, time, 4) float32: the kernels write `out` directly
             if timed:
                 e[1].record()
                 kev.append(e)
-            shard.unstage(out)
+            shard.unstage(out)      # (a no-op then)
 
         def collect_blocks():
             for i, s in enumerate(samples):

@@ -165,6 +165,13 @@ int ndnlm_run_scratch(const ndnlm_plan_t* plan, const void* padded, void* out_in
 int ndnlm_unstage(const ndnlm_plan_t* plan, const void* out_internal,
                   void* output, const int64_t out_strides[4], void* stream);
 
+/* 1 when a caller array with these element strides already HAS the layout of the internal output buffer (four
+ * variables of the compute type, contiguous behind the axes in the plan's staged order -- e.g. a C-ordered
+ * (y, x, time, 4) float32 cube): ndnlm_run may then be given the caller's `output` (16- / 32-byte aligned) as
+ * `out_internal` and ndnlm_unstage skipped -- the in-place write of nd/_filters.pyx:420 without a second copy of the
+ * cube.  ndnlm_apply does this itself.  0 otherwise. */
+int ndnlm_output_is_native(const ndnlm_plan_t* plan, const int64_t out_strides[4]);
+
 /*
  * One-call form of the reference entry point on device arrays: stage + run + unstage on `stream`,
  * then synchronises the stream and returns NDNLM_ENOSOLUTION / NDNLM_WUNDERFLOW according to the flag.

@@ -26,7 +26,7 @@ KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "tiled": KERNEL_TILED
 # every symbol include/ndnlm.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "ndnlm_plan_create", "ndnlm_plan_create_roles", "ndnlm_plan_destroy", "ndnlm_plan_info", "ndnlm_stage", "ndnlm_halo_bytes",
-    "ndnlm_halo_pack", "ndnlm_halo_unpack", "ndnlm_run", "ndnlm_run_scratch", "ndnlm_scratch_bytes", "ndnlm_unstage", "ndnlm_workspace_bytes",
+    "ndnlm_halo_pack", "ndnlm_halo_unpack", "ndnlm_run", "ndnlm_run_scratch", "ndnlm_scratch_bytes", "ndnlm_unstage", "ndnlm_output_is_native", "ndnlm_workspace_bytes",
     "ndnlm_apply", "ndnlm_synth_cube", "ndnlm_measure_fp32_peak", "ndnlm_launch_count", "ndnlm_last_error", "ndnlm_version",
 ]
 # every symbol include/ndflt.h declares (sibling filters)
@@ -100,6 +100,8 @@ def lib():
     L.ndnlm_scratch_bytes.restype = ctypes.c_size_t
     L.ndnlm_unstage.argtypes = [vp, vp, vp, i64p, vp]
     L.ndnlm_unstage.restype = ctypes.c_int
+    L.ndnlm_output_is_native.argtypes = [vp, i64p]
+    L.ndnlm_output_is_native.restype = ctypes.c_int
     L.ndnlm_workspace_bytes.argtypes = [vp]
     L.ndnlm_workspace_bytes.restype = ctypes.c_size_t
     L.ndnlm_apply.argtypes = [vp, vp, i64p, vp, i64p, vp, vp]

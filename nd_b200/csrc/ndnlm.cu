@@ -186,7 +186,7 @@ struct ndnlm_plan {
 
 static const size_t kMaxSmem = 232448;   // 227 KB per CTA on sm_100a
 #ifndef NDNLM_DH_MIN_FW
-#define NDNLM_DH_MIN_FW 2                // double-duty-halo-warp instantiations are preferred from this W patch radius on
+#define NDNLM_DH_MIN_FW 2                // float32: double-duty-halo-warp instantiations are preferred from this W patch radius on
 #endif
 
 static int largest_divisor_leq(int n, int cap) {
@@ -373,14 +373,15 @@ extern "C" int ndnlm_plan_create_roles(ndnlm_plan_t** out_plan, const int64_t sh
         const char* venv = getenv("NDNLM_TILED_VARIANT");   // tuning aid: force one instantiation
         const int forced = venv ? atoi(venv) : -1;
         // Two rounds over the table: the double-duty-halo-warp instantiations (instances_g6.inc) first where they are
-        // enabled (by default for patch radius f_W >= NDNLM_DH_MIN_FW; NDNLM_DH=0 / 1 disables / enables all of them),
-        // then everything else in file order.
+        // enabled (by default for patch radius f_W >= NDNLM_DH_MIN_FW and for float64; NDNLM_DH=0 / 1 disables /
+        // enables all of them), then everything else in file order.
         const char* denv = getenv("NDNLM_DH");
         for (int round = 0; round < 2 && pl->inst < 0; ++round) {
             for (int i = 0; i < g_ntiled; ++i) {
                 if (forced >= 0 && i != forced) continue;
-                // measured (profiles/r2_dh_*): +15 % with four halo rows (f_W = 2), -1 % with two (f_W = 1)
-                const bool use_dh = denv ? atoi(denv) != 0 : (g_tiled[i].fw >= NDNLM_DH_MIN_FW);
+                // measured (profiles/r2_dh_experiment*.txt): float32 +15 % with four halo rows (f_W = 2), -1 % with two
+                // (f_W = 1: that kernel is bound by the shared-memory pipe, not by latency); float64 +9 % / +24 %
+                const bool use_dh = denv ? atoi(denv) != 0 : (g_tiled[i].fw >= NDNLM_DH_MIN_FW || g_tiled[i].elem == 8);
                 if (forced < 0 && (g_tiled[i].dh != (round == 0) || (g_tiled[i].dh && !use_dh))) continue;
                 if (configure_tiled(pl, g_tiled[i], elem)) {
                     pl->kernel = NDNLM_KERNEL_TILED;
@@ -501,7 +502,28 @@ extern "C" int ndnlm_stage(const ndnlm_plan_t* pl, const void* arr, const int64_
         S.hi_halo = hi_edge;
     }
     const long long pvox = (long long)S.pd[0] * S.pd[1] * S.pd[2];
-    if (pl->kernel == NDNLM_KERNEL_TILED) {
+    static const bool legacy_stage = getenv("NDNLM_STAGE") && strcmp(getenv("NDNLM_STAGE"), "legacy") == 0;   // debugging aid
+    const long long xr_plane = (long long)S.pd[1] * S.pd[2];
+    if (pl->kernel == NDNLM_KERNEL_TILED && !legacy_stage && xr_plane < (1LL << 31)) {
+        // row-blocked staging kernel; one vector load per voxel when the caller's layout allows it
+        const size_t vb = size_t(pl->vec_bytes);
+        const bool same_type = (pl->dtype == NDNLM_F64) == (pl->vec_bytes == 32);
+        bool vec = same_type && S.V % 4 == 0 && S.vstride == 1 && (reinterpret_cast<uintptr_t>(arr) % vb) == 0;
+        for (int k = 0; k < 3; ++k)
+            if (S.pd[k] > 1 && S.rstride[k] % 4 != 0) vec = false;
+        const unsigned wblocks = unsigned((S.pd[0] + STAGE_ROWS - 1) / STAGE_ROWS);
+        const dim3 grid(unsigned((xr_plane + 255) / 256), wblocks < 65535u ? wblocks : 65535u, unsigned(S.nv4));
+#define NDNLM_STAGE_ROWS(TIN, V4, VEC) \
+        stage_tiled_rows_kernel<TIN, V4, VEC><<<grid, 256, 0, st>>>(S, (const TIN*)arr, (V4*)padded, wblocks)
+        if (pl->vec_bytes == 32) {
+            if (vec) NDNLM_STAGE_ROWS(double, double4v, true); else NDNLM_STAGE_ROWS(double, double4v, false);
+        } else if (pl->dtype == NDNLM_F64) {
+            NDNLM_STAGE_ROWS(double, float4, false);
+        } else {
+            if (vec) NDNLM_STAGE_ROWS(float, float4, true); else NDNLM_STAGE_ROWS(float, float4, false);
+        }
+#undef NDNLM_STAGE_ROWS
+    } else if (pl->kernel == NDNLM_KERNEL_TILED) {
         const long long total = pvox * S.nv4;
         if (pl->vec_bytes == 32)
             stage_tiled_kernel<double, double4v><<<blocks_for(total, 256), 256, 0, st>>>(S, (const double*)arr, (double4v*)padded);
@@ -519,6 +541,24 @@ extern "C" int ndnlm_stage(const ndnlm_plan_t* pl, const void* arr, const int64_
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return NDNLM_OK;
+}
+
+// The internal output of the tiled kernels is [q][W][X][R] vectors of 4 variables.  With exactly 4 variables of the
+// compute type and a caller array whose strides spell that order, it IS the caller's array.
+extern "C" int ndnlm_output_is_native(const ndnlm_plan_t* pl, const int64_t out_strides[4]) {
+    if (!pl || !out_strides || pl->kernel != NDNLM_KERNEL_TILED) return 0;
+    const DevParams& P = pl->P;
+    if (P.V != 4 || P.nv4 != 1) return 0;
+    if ((pl->dtype == NDNLM_F64) != (pl->vec_bytes == 32)) return 0;      // float64 data computed in float32
+    const int order[3] = {ROLE_R, ROLE_X, ROLE_W};                          // fastest first, behind the variables
+    long long expect = 4;
+    if (out_strides[3] != 1) return 0;
+    for (int k = 0; k < 3; ++k) {
+        const int role = order[k];
+        if (P.n[role] > 1 && out_strides[pl->perm[role]] != expect) return 0;
+        expect *= P.n[role];
+    }
+    return 1;
 }
 
 extern "C" int ndnlm_unstage(const ndnlm_plan_t* pl, const void* internal, void* output, const int64_t out_strides[4],
@@ -717,10 +757,16 @@ extern "C" int ndnlm_apply(const ndnlm_plan_t* pl, const void* arr, const int64_
     int rc = ndnlm_stage(pl, arr, arr_strides, padded, -1, NDNLM_EDGE_REFLECT, NDNLM_EDGE_REFLECT, stream);
     if (rc) return rc;
     void* scratch = ndnlm_scratch_bytes(pl) ? (void*)(ws + align256(pl->padded_bytes) + align256(pl->out_bytes) + 256) : nullptr;
-    rc = ndnlm_run_scratch(pl, padded, internal, flag, scratch, stream);
-    if (rc) return rc;
-    rc = ndnlm_unstage(pl, internal, output, out_strides, stream);
-    if (rc) return rc;
+    if (output && out_strides && ndnlm_output_is_native(pl, out_strides) &&
+        (reinterpret_cast<uintptr_t>(output) % size_t(pl->vec_bytes)) == 0) {
+        rc = ndnlm_run_scratch(pl, padded, output, flag, scratch, stream);      // the kernels write the caller's array
+        if (rc) return rc;
+    } else {
+        rc = ndnlm_run_scratch(pl, padded, internal, flag, scratch, stream);
+        if (rc) return rc;
+        rc = ndnlm_unstage(pl, internal, output, out_strides, stream);
+        if (rc) return rc;
+    }
     int32_t hflag = 0;
     CUDA_TRY(cudaMemcpyAsync(&hflag, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

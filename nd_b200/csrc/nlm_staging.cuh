@@ -62,6 +62,70 @@ __global__ void stage_tiled_kernel(const StageParams S, const TIN* __restrict__ 
     padded[i] = mk4(v[0], v[1], v[2], v[3]);
 }
 
+// Source offset contribution of one role for padded index `ip` (the rule of stage_tiled_kernel above): reflection
+// (reference `_idx`), or -- on the shard axis -- rows that are left untouched (false is returned) / read from the
+// enclosing array.
+__host__ __device__ inline bool stage_role_offset(const StageParams& S, const int role, const int ip, long long& off) {
+    const int u = ip - S.pad[role];
+    if (role == S.halo_role) {
+        if ((S.lo_halo == 1 && u < 0) || (S.hi_halo == 1 && u >= S.n[role])) return false;
+        if ((S.lo_halo == 2 && u < 0) || (S.hi_halo == 2 && u >= S.n[role])) {
+            off += (long long)u * S.rstride[role];
+            return true;
+        }
+    }
+    off += (long long)reflect_index(u, S.n[role]) * S.rstride[role];
+    return true;
+}
+
+// One thread of stage_tiled_rows_kernel (also run on the host by tools/emu_stage.cu, which checks it against
+// stage_tiled_kernel's rule element by element): thread `j` of the (X, R) plane stages STAGE_ROWS consecutive W rows.
+constexpr int STAGE_ROWS = 4;
+template <typename TIN, typename V4, bool VEC>
+__host__ __device__ inline void stage_tiled_rows_thread(const StageParams& S, const TIN* __restrict__ arr,
+                                                        V4* __restrict__ padded, const unsigned j, const unsigned wblock,
+                                                        const int q) {
+    using TS = decltype(V4().x);
+    const unsigned pdr = unsigned(S.pd[1]), pdx = unsigned(S.pd[2]);
+    if (j >= pdr * pdx) return;
+    const unsigned x = j / pdr, r = j - x * pdr;            // R is the fastest axis of the staged cube
+    long long off_xr = (long long)(4 * q) * S.vstride;
+    if (!stage_role_offset(S, ROLE_X, int(x), off_xr)) return;
+    if (!stage_role_offset(S, ROLE_R, int(r), off_xr)) return;
+    const int w0 = int(wblock) * STAGE_ROWS;
+    V4 v[STAGE_ROWS];
+    bool ok[STAGE_ROWS];
+#pragma unroll
+    for (int k = 0; k < STAGE_ROWS; ++k) {
+        long long src = off_xr;
+        ok[k] = (w0 + k < S.pd[0]) && stage_role_offset(S, ROLE_W, w0 + k, src);
+        if (!ok[k]) continue;
+        if constexpr (VEC) {
+            v[k] = *reinterpret_cast<const V4*>(arr + src);   // 4 consecutive variables, 16 / 32-byte aligned (host check)
+        } else {
+            TS t[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) t[c] = (4 * q + c < S.V) ? TS(arr[src + c * S.vstride]) : TS(0);
+            v[k].x = t[0]; v[k].y = t[1]; v[k].z = t[2]; v[k].w = t[3];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < STAGE_ROWS; ++k)
+        if (ok[k]) padded[((size_t(q) * S.pd[0] + (w0 + k)) * pdx + x) * pdr + r] = v[k];
+}
+
+// The staging kernel of the tiled layout: the same result as stage_tiled_kernel, with 32-bit index arithmetic done once
+// per STAGE_ROWS elements and one vector load per voxel where the caller's array allows it (VEC: the variables are
+// contiguous, a multiple of 4, and every voxel starts on a 16- / 32-byte boundary).  grid = ((X R plane) / 256,
+// ceil(pd_W / STAGE_ROWS) [folded into y and z], nv4 [z]).
+template <typename TIN, typename V4, bool VEC>
+__global__ void __launch_bounds__(256) stage_tiled_rows_kernel(const StageParams S, const TIN* __restrict__ arr,
+                                                               V4* __restrict__ padded, const unsigned wblocks) {
+    const unsigned j = blockIdx.x * 256u + threadIdx.x;
+    const int q = int(blockIdx.z);
+    for (unsigned wb = blockIdx.y; wb < wblocks; wb += gridDim.y) stage_tiled_rows_thread<TIN, V4, VEC>(S, arr, padded, j, wb, q);
+}
+
 template <typename T>
 __global__ void stage_generic_kernel(const StageParams S, const T* __restrict__ arr, T* __restrict__ padded) {
     const long long total = (long long)S.pd[0] * S.pd[1] * S.pd[2] * S.V;

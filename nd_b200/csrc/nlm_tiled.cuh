@@ -660,7 +660,7 @@ nlm_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const DevParams P,
                     for (int q = 0; q < NV4; ++q) n[q][k] = nb[size_t(q) * plane + k];
                 // my readers must be done with the previous round before its slots are overwritten
                 if constexpr (!NDNLM_DEBUG_CTA_SYNC) mbar_wait(mbar_empty + hrow, par ^ 1);
-                P2* const ex = exch + (hrow * (L / 2)) * 32 + lane;
+                [[maybe_unused]] P2* const ex = exch + (hrow * (L / 2)) * 32 + lane;
                 [[maybe_unused]] V4* const ex4 = reinterpret_cast<V4*>(exch) + hrow * 32 + lane;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {

@@ -149,6 +149,26 @@ class Plan:
         _lib.check(self._L.ndnlm_unstage(self._h, ctypes.c_void_p(internal_out.data_ptr()),
                                          ctypes.c_void_p(output.data_ptr()), _lib.i64(output.stride()), self._stream(internal_out)))
 
+    def output_is_native(self, output):
+        """True when `output` already has the layout (and alignment) of the internal output buffer, so that the
+        kernels can write it directly (ndnlm_output_is_native) -- no second copy of the cube, no unstage pass."""
+        return (tuple(output.shape) == self.shape and output.dtype == self.torch_dtype
+                and output.data_ptr() % (4 * output.element_size()) == 0
+                and bool(self._L.ndnlm_output_is_native(self._h, _lib.i64(output.stride()))))
+
+    def run_into(self, padded, output, err_flag, internal_out=None, scratch=None):
+        """run + unstage: straight into `output` when its layout allows it, through `internal_out` (allocated when
+        None) otherwise.  Returns True when the direct route was taken."""
+        self._check_arr(output)
+        if self.output_is_native(output):
+            self.run(padded, output, err_flag, scratch)
+            return True
+        if internal_out is None:
+            internal_out = self.new_internal_out(padded.device)
+        self.run(padded, internal_out, err_flag, scratch)
+        self.unstage(internal_out, output)
+        return False
+
     def apply(self, arr, output=None, workspace=None):
         """ndnlm_apply: stage + run + unstage on the current stream; raises ValueError('No solution')."""
         self._check_arr(arr)

@@ -114,7 +114,7 @@ def exchange_halos_dist(send_lo, send_hi, recv_lo, recv_hi, rank, world, group=N
 class DistributedShard:
     """One rank's share of a y-sharded apply (one process per GPU).
 
-    Usage per apply:  stage(slab) -> exchange() -> run() -> unstage(out_slab)."""
+    Usage per apply:  stage(slab) -> exchange() -> run([out_slab]) -> unstage(out_slab)."""
 
     def __init__(self, plan, axis, rank, world, group=None):
         self.plan, self.axis, self.rank, self.world, self.group = plan, axis, rank, world, group
@@ -122,7 +122,8 @@ class DistributedShard:
         self.hi_edge = 'reflect' if rank == world - 1 else 'halo'
         dev = torch.device('cuda', torch.cuda.current_device())
         self.padded = plan.new_padded(dev)
-        self.internal = plan.new_internal_out(dev)
+        self.internal = None           # allocated on first use: output slabs with the kernels' own layout never need it
+        self._direct = False
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         nbytes = plan.halo_bytes(axis)
         mk = lambda: torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -146,8 +147,17 @@ class DistributedShard:
             self.plan.halo_unpack(self.padded, self.axis, 1, self.recv_hi)
         return n
 
-    def run(self):
+    def run(self, out_slab=None):
+        """Run the kernels.  With `out_slab` given and laid out like the internal output (Plan.output_is_native) they
+        write it directly and `unstage` becomes a no-op; otherwise the result waits in the internal buffer."""
+        self._direct = out_slab is not None and self.plan.output_is_native(out_slab)
+        if self._direct:
+            self.plan.run(self.padded, out_slab, self.flag)
+            return
+        if self.internal is None:
+            self.internal = self.plan.new_internal_out(self.padded.device)
         self.plan.run(self.padded, self.internal, self.flag)
 
     def unstage(self, out_slab):
-        self.plan.unstage(self.internal, out_slab)
+        if not self._direct:
+            self.plan.unstage(self.internal, out_slab)

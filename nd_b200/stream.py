@@ -163,7 +163,7 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
             pad_bytes = max(pad_bytes, plans[shape].padded_bytes)
             out_bytes = max(out_bytes, plans[shape].out_bytes)
     padded = [torch.empty(pad_bytes, dtype=torch.uint8, device=device) for _ in range(2)]
-    internal = [torch.empty(out_bytes, dtype=torch.uint8, device=device) for _ in range(2)]
+    internal = [None, None]        # internal output buffers: only for output slabs the kernels cannot write in place
     flag = torch.zeros(1, dtype=torch.int32, device=device)
 
     cur = torch.cuda.current_stream()
@@ -228,8 +228,9 @@ def apply_host_pipelined(arr, output, r3, f3, sigma, h, n_eff=-1, semantics=None
                 a_out.copy_(a_in)
             else:
                 plan.stage(a_in, padded[b], 0, 'reflect' if lo == 0 else 'source', 'reflect' if hi == n0 else 'source')
-                plan.run(padded[b], internal[b], flag)
-                plan.unstage(internal[b], a_out)
+                if internal[b] is None and not plan.output_is_native(a_out):
+                    internal[b] = torch.empty(out_bytes, dtype=torch.uint8, device=device)
+                plan.run_into(padded[b], a_out, flag, internal[b])
             ev_comp = torch.cuda.Event()
             ev_comp.record(s_comp)
             ev_in_free[b] = ev_comp
@@ -310,7 +311,7 @@ def apply_device_streamed(source, sink, n0, inner_shape, r3, f3, sigma, h, n_eff
             plans[hi - lo] = dev.Plan((hi - lo,) + inner_shape, r3, f3, sigma, h, n_eff, semantics=semantics,
                                       dtype=dtype, kernel=kernel)
     padded = torch.empty(max(p.padded_bytes for p in plans.values()), dtype=torch.uint8, device=device)
-    internal = torch.empty(max(p.out_bytes for p in plans.values()), dtype=torch.uint8, device=device)
+    internal = None                # internal output buffer: only when the kernels cannot write the output slab in place
     flag = torch.zeros(1, dtype=torch.int32, device=device)
     for lo, hi in sp.ranges:
         # rows below: the neighbour shard's rows at the shard edge, rows of this cube otherwise (none at a true edge)
@@ -330,10 +331,14 @@ def apply_device_streamed(source, sink, n0, inner_shape, r3, f3, sigma, h, n_eff
         plan.stage(a_in, padded, 0, 'source' if below else 'reflect', 'source' if above else 'reflect')
         if on_kernel is not None:
             on_kernel(True, plan)
-        plan.run(padded, internal, flag)
+        direct = plan.output_is_native(a_out)          # C-ordered slabs of 4 variables: the kernels write them in place
+        if not direct and internal is None:
+            internal = torch.empty(max(p.out_bytes for p in plans.values()), dtype=torch.uint8, device=device)
+        plan.run(padded, a_out if direct else internal, flag)
         if on_kernel is not None:
             on_kernel(False, plan)
-        plan.unstage(internal, a_out)
+        if not direct:
+            plan.unstage(internal, a_out)
         sink(lo, hi, a_out)
     _lib.check_flag(flag.item())
     return sp.nshards

@@ -304,6 +304,42 @@ def test_double_duty_halo_warps_equal_plain_instantiations_bitwise(dev, monkeypa
     assert scaled_err(dh, c_port.nlmeans(a, r, f, 0.3, 0.6)) < (TOL64 if dtype == np.float64 else TOL32)
 
 
+@pytest.mark.parametrize("dtype,sem", [(np.float32, "as_written"), (np.float64, "as_written"), (np.float32, "reference_compiled")])
+def test_kernels_write_a_native_output_in_place(dev, dtype, sem):
+    """A C-ordered (y, x, time, 4) output already has the kernels' own output layout (ndnlm_output_is_native): it is
+    written directly, bitwise equal to the route through the internal buffer + unstage (taken for any other layout),
+    for the one-call ndnlm_apply, Plan.run_into and the device slab streaming."""
+    import torch
+    from nd_b200 import stream
+    a = sar_like((41, 50, 12, 4), seed=31, dtype=dtype)
+    r, f = (3, 2, 1), (1, 1, 1)
+    d_in = torch.from_numpy(a).cuda()
+    plan = dev.Plan(a.shape, r, f, 0.3, 0.6, semantics=sem, dtype=dtype)
+    out_native = torch.full_like(d_in, float("nan"))
+    assert plan.output_is_native(out_native)
+    plan.apply(d_in, out_native)
+    vmajor = torch.empty((4,) + a.shape[:3], dtype=d_in.dtype, device="cuda").permute(1, 2, 3, 0)     # not native
+    assert not plan.output_is_native(vmajor)
+    plan.apply(d_in, vmajor)
+    assert torch.equal(out_native, vmajor)
+    assert not plan.output_is_native(torch.empty((a.shape[0], a.shape[1], a.shape[2] + 1, 4), dtype=d_in.dtype, device="cuda")[:, :, 1:])  # shape ok, rows not dense
+    # run_into: direct and through the internal buffer
+    padded = plan.new_padded("cuda"); flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    plan.stage(d_in, padded)
+    o2 = torch.full_like(d_in, float("nan"))
+    assert plan.run_into(padded, o2, flag) is True and torch.equal(o2, out_native)
+    o3 = torch.empty((4,) + a.shape[:3], dtype=d_in.dtype, device="cuda").permute(1, 2, 3, 0)
+    assert plan.run_into(padded, o3, flag) is False and torch.equal(o3, out_native)
+    # device slab streaming writes its (contiguous) output slabs in place
+    got = torch.full_like(d_in, float("nan"))
+    stream.apply_device_streamed(lambda lo, hi, dst: dst.copy_(d_in[lo:hi]), lambda lo, hi, res: got[lo:hi].copy_(res),
+                                 a.shape[0], a.shape[1:], r, f, 0.3, 0.6, semantics=sem, slab_rows=16, dtype=dtype)
+    assert torch.equal(got, out_native)
+    from oracle import c_port
+    tol = TOL64 if dtype == np.float64 else (1e-5 if sem == "reference_compiled" else TOL32)
+    assert scaled_err(out_native.cpu().numpy(), c_port.nlmeans(a, r, f, 0.3, 0.6, semantics=sem)) < tol
+
+
 def test_double_duty_halo_warps_n_eff_and_default_choice(dev, monkeypatch):
     from oracle import c_port
     a = sar_like((31, 40, 10, 4), seed=29, dtype=np.float32)

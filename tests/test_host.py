@@ -114,9 +114,57 @@ def test_double_duty_halo_warp_instantiations_are_chosen_for_f2(monkeypatch):
     monkeypatch.setenv("NDNLM_DH", "1")
     p = device.Plan((4096, 4096, 32, 4), (5, 5, 2), (1, 1, 1), 0.25, 0.5)
     assert "(dh)" in p.kernel_name and list(p.info.tile)[0] == 15 and p.info.smem_bytes <= 232448
+    # float64 data: the default for f = 1 and f = 2 (7 / 6 valid rows of 8 warps instead of 6 / 4)
+    monkeypatch.delenv("NDNLM_DH", raising=False)
+    for f, rows in (((1, 1, 1), 7), ((2, 2, 2), 6)):
+        p64 = device.Plan((210, 2048, 32, 4), (5, 5, 2), f, 0.25, 0.5, dtype=np.float64)
+        assert "double" in p64.kernel_name and "(dh)" in p64.kernel_name and list(p64.info.tile)[0] == rows
     # configurations without such an instantiation are unaffected (2-D: no W patch axis; V = 6)
     assert "(dh)" not in device.Plan((1, 206, 500, 4), (0, 3, 3), (0, 1, 1), 1, 1).kernel_name
     assert "(dh)" not in device.Plan((64, 256, 128, 6), (10, 10, 3), (2, 2, 2), 1, 1).kernel_name
+
+
+def test_output_is_native_rule():
+    """ndnlm_output_is_native: a caller array that already has the internal output layout ([W][X][R] vectors of the 4
+    variables) is written by the kernels directly (no unstage pass, no second copy of the cube)."""
+    from nd_b200 import _lib
+    L = _lib.lib()
+    def native(plan, shape, order):
+        strides, acc = [0] * 4, 1
+        for ax in reversed(order):
+            strides[ax] = acc
+            acc *= shape[ax]
+        return bool(L.ndnlm_output_is_native(plan._h, _lib.i64(strides)))
+    shape = (64, 80, 16, 4)
+    p = device.Plan(shape, (3, 3, 1), (1, 1, 1), 1, 1)
+    assert p.roles == (0, 2, 1)                                   # W = axis 0, R = axis 2, X = axis 1
+    assert native(p, shape, (0, 1, 2, 3))                         # C-ordered (y, x, time, V)
+    assert not native(p, shape, (3, 0, 1, 2))                     # variable-major (what Filter.apply hands over)
+    assert not native(p, shape, (0, 2, 1, 3))                     # time before x
+    assert not native(device.Plan((64, 80, 16, 3), (3, 3, 1), (1, 1, 1), 1, 1), (64, 80, 16, 3), (0, 1, 2, 3))   # V != 4
+    assert not native(device.Plan((64, 80, 16, 8), (3, 3, 1), (1, 1, 1), 1, 1), (64, 80, 16, 8), (0, 1, 2, 3))   # two groups
+    assert native(device.Plan(shape, (3, 3, 1), (1, 1, 1), 1, 1, dtype=np.float64), shape, (0, 1, 2, 3))         # float64 kernel
+    assert not native(device.Plan(shape, (3, 3, 1), (1, 1, 1), 1, 1, dtype=np.float64, kernel="tiled"), shape, (0, 1, 2, 3))
+    assert not native(device.Plan(shape, (3, 3, 1), (1, 1, 1), 1, 1, kernel="generic"), shape, (0, 1, 2, 3))
+    assert native(device.Plan(shape, (3, 3, 1), (1, 1, 1), 1, 1, semantics="reference_compiled"), shape, (0, 1, 2, 3))  # box mean
+    # 2-D image behind a singleton axis: the stride of an extent-1 axis is irrelevant
+    p2 = device.Plan((1, 206, 500, 4), (0, 3, 3), (0, 1, 1), 1, 1)
+    ok = [native(p2, (1, 206, 500, 4), o) for o in ((0, 1, 2, 3), (0, 2, 1, 3))]
+    assert ok.count(True) == 1                                    # exactly the order that matches its X / R roles
+
+
+def test_staging_kernel_emulated_on_the_host(tmp_path):
+    """tools/emu_stage.cu runs every thread of the row-blocked staging kernel on the CPU and compares the staged cube
+    with the rule of the one-thread-per-element kernel it replaced (4160 layouts / edge modes / V / dtypes)."""
+    import shutil, subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc is not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "emu_stage")
+    subprocess.run(["nvcc", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-w", "-o", exe,
+                    os.path.join(root, "tools", "emu_stage.cu")], check=True, capture_output=True, timeout=600)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and " 0 mismatching elements" in p.stdout, p.stdout + p.stderr
 
 
 def test_plan_errors_map_to_reference_exceptions():
