@@ -334,7 +334,12 @@ def test_kernels_write_a_native_output_in_place(dev, dtype, sem):
     got = torch.full_like(d_in, float("nan"))
     stream.apply_device_streamed(lambda lo, hi, dst: dst.copy_(d_in[lo:hi]), lambda lo, hi, res: got[lo:hi].copy_(res),
                                  a.shape[0], a.shape[1:], r, f, 0.3, 0.6, semantics=sem, slab_rows=16, dtype=dtype)
-    assert torch.equal(got, out_native)
+    if sem == "reference_compiled":
+        # the box-mean kernels update their running sums along march segments that depend on the slab height: a slab
+        # agrees with the whole cube to rounding, not bitwise
+        assert scaled_err(got.cpu().numpy(), out_native.cpu().numpy()) < 1e-5
+    else:
+        assert torch.equal(got, out_native)
     from oracle import c_port
     tol = TOL64 if dtype == np.float64 else (1e-5 if sem == "reference_compiled" else TOL32)
     assert scaled_err(out_native.cpu().numpy(), c_port.nlmeans(a, r, f, 0.3, 0.6, semantics=sem)) < tol
