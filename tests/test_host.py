@@ -155,7 +155,7 @@ def test_output_is_native_rule():
 
 def test_staging_kernel_emulated_on_the_host(tmp_path):
     """tools/emu_stage.cu runs every thread of the row-blocked staging kernel on the CPU and compares the staged cube
-    with the rule of the one-thread-per-element kernel it replaced (4160 layouts / edge modes / V / dtypes)."""
+    with the rule of the one-thread-per-element kernel it replaced (8960 layouts / edge modes / V / dtypes)."""
     import shutil, subprocess
     if shutil.which("nvcc") is None:
         pytest.skip("nvcc is not on PATH")

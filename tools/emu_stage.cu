@@ -82,8 +82,8 @@ int main() {
         for (int o = 0; o < 3; ++o)
             for (int V = 1; V <= 8; ++V)
                 for (int hr = -1; hr < 3; ++hr)
-                    for (int mode = 0; mode < (hr < 0 ? 1 : 4); ++mode) {
-                        const int lo = mode == 0 ? 0 : mode == 1 ? 1 : mode == 2 ? 2 : 2, hi = mode == 0 ? 0 : mode == 1 ? 1 : mode == 2 ? 2 : 0;
+                    for (int mode = 0; mode < (hr < 0 ? 1 : 9); ++mode) {     // every (lo, hi) pair of reflect / halo / source
+                        const int lo = mode / 3, hi = mode % 3;
                         const int margin = hr >= 0 ? pads[s][hr] : 0;
                         bad += run_case<float, float4, false>(shapes[s], pads[s], V, orders[o], hr, lo, hi, margin);
                         bad += run_case<double, double4v, false>(shapes[s], pads[s], V, orders[o], hr, lo, hi, margin);
